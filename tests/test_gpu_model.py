@@ -1,0 +1,167 @@
+"""GPU parity of the whole path through the reference-facing nn.Module surface: logits, every
+parameter gradient and one clip+AdamW step, against the golden vectors produced by the unmodified
+reference (tests/golden/) and against the numpy oracle at larger shapes.
+
+Tolerances (BASELINE.json north_star / SURVEY Appendix B):
+  fp32 path: logits 1e-4 relative; per-tensor gradient L2-rel 1e-3; w_k.bias absolute (dead parameter)
+  bf16 path: logits 2e-2 relative; per-tensor gradient L2-rel 6e-2, global 3e-2"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN_CASES, GOLDEN_HP, l2_rel, load_golden, rel_err  # noqa: E402
+from oracle import amc_oracle as O  # noqa: E402
+
+import vit_vs_raw_iq_b200 as amc  # noqa: E402
+
+DEV = "cuda:0"
+LOGIT_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+GRAD_TOL = {"fp32": 1e-3, "bf16": 6e-2}
+GLOBAL_GRAD_TOL = {"fp32": 2e-4, "bf16": 3e-2}
+
+
+def build(name, dtype, drop=0.0):
+    kind, kw = GOLDEN_CASES[name]
+    cls = amc.RawIQAMCTransformer if kind == "rawiq" else amc.ViTAMCTransformer
+    return cls(**kw, drop_prob=drop, device=DEV, compute_dtype=dtype)
+
+
+def bf16_supported(name):
+    kind, kw = GOLDEN_CASES[name]
+    K = kw["in_channels"] * (kw["patch_size"] ** 2 if kind == "vit" else
+                             (1 if kw["embedding_type"] == "conv1d" else kw["segment_size"]))
+    return K % 8 == 0 and kw["d_model"] % 8 == 0
+
+
+def check_grads(model, ref_grads, dtype):
+    gmax = max(np.abs(v).max() for v in ref_grads.values())
+    num = den = 0.0
+    for n, p in model.named_parameters():
+        g = p.grad.detach().cpu().numpy()
+        r = ref_grads[n]
+        assert g.shape == r.shape, n
+        if n.endswith("w_k.bias"):
+            assert np.abs(g).max() <= (1e-6 if dtype == "fp32" else 2e-3) * gmax, n
+            continue
+        e = l2_rel(g, r)
+        assert e < GRAD_TOL[dtype], (n, e)
+        num += float(((g.astype(np.float64) - r) ** 2).sum())
+        den += float((r.astype(np.float64) ** 2).sum())
+    assert (num / den) ** 0.5 < GLOBAL_GRAD_TOL[dtype]
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_golden_logits_grads_and_train_step(name, dtype):
+    if dtype == "bf16" and not bf16_supported(name):
+        pytest.skip("bf16 path needs a patch width that is a multiple of 8")
+    z, params, grads, after = load_golden(name)
+    model = build(name, dtype)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    model.train()
+    src = torch.from_numpy(z["src"]).to(DEV)
+    labels = torch.from_numpy(z["labels"]).to(DEV)
+    # the reference training step, verbatim (R/training/train.py:258-271)
+    opt = torch.optim.AdamW(model.parameters(), lr=GOLDEN_HP["lr"], weight_decay=GOLDEN_HP["weight_decay"],
+                            betas=GOLDEN_HP["betas"])
+    opt.zero_grad()
+    out = model(src)
+    loss = torch.nn.CrossEntropyLoss(label_smoothing=GOLDEN_HP["label_smoothing"])(out, labels)
+    loss.backward()
+    assert out.shape == z["logits"].shape
+    assert rel_err(out.detach().cpu().numpy(), z["logits"]) < LOGIT_TOL[dtype]
+    assert abs(loss.item() - float(z["loss"])) < (1e-4 if dtype == "fp32" else 2e-2)
+    check_grads(model, grads, dtype)
+    total = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=GOLDEN_HP["clip"])
+    assert abs(total.item() - float(z["grad_norm"])) / float(z["grad_norm"]) < (1e-4 if dtype == "fp32" else 3e-2)
+    opt.step()
+    if dtype == "fp32":
+        for n, p in model.named_parameters():
+            upd = p.detach().cpu().numpy() - params[n]
+            ref_upd = after[n] - params[n]
+            if n.endswith("w_k.bias"):
+                continue   # Adam normalises a ~1e-10 gradient to a +-lr step: sign of noise, not comparable
+            assert np.abs(upd - ref_upd).max() < 1e-5 + 2e-2 * np.abs(ref_upd).max(), n
+    # the encoder output (model.encoder(src)) must match too
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    model.eval()
+    with torch.no_grad():
+        enc = model.encoder(src)
+    assert rel_err(enc.cpu().numpy(), z["enc_out"]) < LOGIT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind,kw,B", [
+    ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8, n_layers=3,
+                   ffn_hidden=512, use_cls_token=True, embedding_type="segment", segment_size=16), 16),
+    ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19, d_model=256, n_head=8,
+                 n_layers=2, ffn_hidden=1024), 33),
+    ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=4, num_classes=19, d_model=128, n_head=8,
+                 n_layers=2, ffn_hidden=512), 7),
+    ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=256, n_head=8, n_layers=1,
+                   ffn_hidden=1024, use_cls_token=True, embedding_type="segment", segment_size=8), 3),
+])
+def test_oracle_parity_at_reference_shapes(kind, kw, B, dtype):
+    """cfg-1-like, cfg-2 (ViT p16 d256), production ViT and the SPS-2 (L=2048, T=257) shapes vs the oracle."""
+    torch.manual_seed(3)
+    cls = amc.RawIQAMCTransformer if kind == "rawiq" else amc.ViTAMCTransformer
+    model = cls(**kw, drop_prob=0.0, device=DEV, compute_dtype=dtype)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith(("gamma", "beta", "mlp_head.0.weight", "mlp_head.0.bias")):
+                p.add_(0.1 * torch.randn_like(p))
+    shape = (B, 2, kw["seq_length"]) if kind == "rawiq" else (B, 1, 32, 64)
+    src = torch.randn(*shape, device=DEV)
+    labels = torch.randint(0, kw["num_classes"], (B,), device=DEV)
+    out = model(src)
+    torch.nn.functional.cross_entropy(out, labels, label_smoothing=0.1).backward()
+    cfg = O.Config(kind=kind, **kw)
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    ref_logits, _, ref_g = O.loss_and_grads(src.cpu().numpy(), labels.cpu().numpy(), params, cfg)
+    assert rel_err(out.detach().cpu().numpy(), ref_logits) < LOGIT_TOL[dtype]
+    check_grads(model, ref_g, dtype)
+
+
+def test_raw_interleaved_input_matches_dataset_preprocessing():
+    """a1/a2: feeding dataset-layout frames + the 4 z-score scalars == preprocessing on the host first."""
+    rng = np.random.default_rng(5)
+    raw = (rng.standard_normal((6, 1024, 2)) * 0.76 + 0.02).astype(np.float32)
+    stats = O.normalization_stats(raw)
+    xn = O.normalize_iq(raw, stats)
+    for kind in ("rawiq", "vit"):
+        torch.manual_seed(1)
+        if kind == "rawiq":
+            model = amc.RawIQAMCTransformer(in_channels=2, seq_length=1024, num_classes=11, d_model=64, n_head=4,
+                                            n_layers=1, ffn_hidden=128, drop_prob=0.0, device=DEV, segment_size=16,
+                                            compute_dtype="fp32")
+            framed = O.frame_rawiq(xn)
+        else:
+            model = amc.ViTAMCTransformer(in_channels=1, img_size_h=32, img_size_w=64, patch_size=8, num_classes=19,
+                                          d_model=64, n_head=4, n_layers=1, ffn_hidden=128, drop_prob=0.0,
+                                          device=DEV, compute_dtype="fp32")
+            framed = O.frame_vit(xn)
+        model.eval()
+        with torch.no_grad():
+            a = model(torch.from_numpy(framed).to(DEV))
+            model.set_raw_input(stats)
+            b = model(torch.from_numpy(raw).to(DEV))
+            model.set_raw_input(None)
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+
+
+def test_batch_sizes_and_eval_determinism():
+    """R/test_model.py:91-92,110-114: output shape (B, num_classes) for B in {1,4,8,16}; eval is deterministic."""
+    torch.manual_seed(0)
+    model = amc.RawIQAMCTransformer(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8,
+                                    n_layers=2, ffn_hidden=512, drop_prob=0.1, device=DEV, use_cls_token=True,
+                                    embedding_type="segment", segment_size=64, compute_dtype="fp32")
+    model.eval()
+    with torch.no_grad():
+        for B in (1, 4, 8, 16):
+            x = torch.randn(B, 2, 1024, device=DEV)
+            y1, y2 = model(x), model(x)
+            assert y1.shape == (B, 11)
+            assert torch.equal(y1, y2)
+        assert model(torch.zeros(0, 2, 1024, device=DEV)).shape == (0, 11)

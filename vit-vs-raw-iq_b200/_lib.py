@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI in include/amc_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is
+no fallback: if the library is missing the import fails, and every call that returns non-zero
+raises ``RuntimeError(amc_last_error())``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libamc_b200.so")
+
+ABI_VERSION = 3
+KIND_RAWIQ, KIND_VIT = 0, 1
+F32, BF16 = 0, 1
+INPUT_MODEL, INPUT_RAW = 0, 1
+
+
+class AmcDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("dtype", C.c_int32), ("B", C.c_int32), ("d", C.c_int32), ("h", C.c_int32),
+        ("F", C.c_int32), ("C", C.c_int32), ("n_layers", C.c_int32), ("in_ch", C.c_int32),
+        ("seq_len", C.c_int32), ("seg", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+        ("patch", C.c_int32), ("has_cls", C.c_int32), ("head_ln", C.c_int32), ("input_layout", C.c_int32),
+        ("training", C.c_int32), ("p_drop", C.c_float), ("ln_eps", C.c_float), ("head_ln_eps", C.c_float),
+        ("norm", C.c_float * 4), ("seed", C.c_uint64), ("offset", C.c_uint64),
+    ]
+
+
+_LAYOUT_I64 = ["total", "emb_w", "emb_b", "cls", "layer0", "layer_stride", "wq", "wk", "wv", "bq", "bk", "bv", "wo",
+               "bo", "g1", "be1", "w1", "b1", "w2", "b2", "g2", "be2", "head_ln_w", "head_ln_b", "head_w", "head_b"]
+
+
+class AmcParamLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in _LAYOUT_I64] + [("T", C.c_int32), ("Ttok", C.c_int32),
+                                                        ("K_embed", C.c_int32), ("pad_", C.c_int32)]
+
+
+class AmcWorkspaceInfo(C.Structure):
+    _fields_ = [("bytes", C.c_size_t), ("saved_bytes", C.c_size_t)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.amc_abi_version.restype = C.c_int
+    lib.amc_last_error.restype = C.c_char_p
+    sigs = {
+        "amc_param_layout": [C.POINTER(AmcDesc), C.POINTER(AmcParamLayout)],
+        "amc_model_workspace": [C.POINTER(AmcDesc), C.POINTER(AmcWorkspaceInfo)],
+        "amc_model_fwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, vp],
+        "amc_model_bwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, i32, i32, vp],
+        "amc_ce_loss": [i32, i32, vp, vp, f32, f32, f32, vp, vp, vp],
+        "amc_adamw_clip_step": [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, i64, vp, vp],
+        "amc_gemm": [i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, vp, i32, i32, vp],
+        "amc_attention_fwd": [i32, i32, i32, i32, i32, vp, vp, vp],
+        "amc_attention_bwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp],
+        "amc_layernorm_fwd": [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp],
+        "amc_layernorm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "amc_frontend_fwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    if lib.amc_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.amc_abi_version()} != expected {ABI_VERSION}; rebuild")
+    return lib, sorted(sigs) + ["amc_abi_version", "amc_last_error"]
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.amc_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what or 'amc_b200'} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device/host address of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def param_layout(desc: AmcDesc) -> AmcParamLayout:
+    out = AmcParamLayout()
+    rc = lib.amc_param_layout(C.byref(desc), C.byref(out))
+    if rc != 0:
+        # constructor-time validation mirrors the reference's ValueError (R/models/encoder.py:45-48)
+        raise ValueError(lib.amc_last_error().decode("utf-8", "replace"))
+    return out
+
+
+def workspace_bytes(desc: AmcDesc) -> int:
+    out = AmcWorkspaceInfo()
+    check(lib.amc_model_workspace(C.byref(desc), C.byref(out)), "amc_model_workspace")
+    return int(out.bytes)

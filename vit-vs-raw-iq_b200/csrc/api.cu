@@ -1,0 +1,582 @@
+// C ABI (include/amc_b200.h): parameter layout, workspace carving and the whole-path
+// forward / backward built from the kernels in this directory.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "attention.cuh"
+#include "gemm_common.cuh"
+#include "rowops.cuh"
+
+namespace amc {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+__global__ void add_inplace_kernel(size_t n, float* __restrict__ a, const float* __restrict__ b) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a[i] += b[i];
+}
+
+struct Dims {
+  int B, T, Ttok, K, d, h, dh, F, C, L, has_cls;
+  int64_t M;  // B*T token rows
+};
+
+int validate(const AmcDesc& D, Dims& m) {
+  AMC_CHECK_ARG(D.kind == AMC_KIND_RAWIQ || D.kind == AMC_KIND_VIT, "unknown model kind %d", D.kind);
+  AMC_CHECK_ARG(D.dtype == AMC_F32 || D.dtype == AMC_BF16, "unknown dtype %d", D.dtype);
+  AMC_CHECK_ARG(D.B >= 0, "batch must be >= 0");
+  AMC_CHECK_ARG(D.d >= 1 && D.d <= 512, "d_model=%d unsupported (1..512)", D.d);
+  AMC_CHECK_ARG(D.h >= 1 && D.d % D.h == 0, "d_model (%d) must be divisible by n_head (%d)", D.d, D.h);
+  AMC_CHECK_ARG(D.d / D.h <= 128, "head dim %d unsupported (<= 128)", D.d / D.h);
+  AMC_CHECK_ARG(D.F >= 1 && D.C >= 1 && D.C <= 64 && D.n_layers >= 0, "bad ffn_hidden/num_classes/n_layers");
+  AMC_CHECK_ARG(D.input_layout == AMC_INPUT_MODEL || D.input_layout == AMC_INPUT_RAW, "bad input_layout");
+  AMC_CHECK_ARG(D.p_drop >= 0.f && D.p_drop < 1.f, "drop_prob must be in [0,1)");
+  m.B = D.B; m.d = D.d; m.h = D.h; m.dh = D.d / D.h; m.F = D.F; m.C = D.C; m.L = D.n_layers;
+  if (D.kind == AMC_KIND_RAWIQ) {
+    AMC_CHECK_ARG(D.in_ch >= 1 && D.seq_len >= 1 && D.seg >= 1, "bad raw-IQ geometry");
+    // R/models/encoder.py:45-48
+    AMC_CHECK_ARG(D.seq_len % D.seg == 0, "seq_length (%d) must be divisible by segment_size (%d)", D.seq_len,
+                  D.seg);
+    AMC_CHECK_ARG(D.input_layout == AMC_INPUT_MODEL || D.in_ch == 2, "raw interleaved input needs in_channels=2");
+    m.Ttok = D.seq_len / D.seg;
+    m.K = D.in_ch * D.seg;
+    m.has_cls = D.has_cls ? 1 : 0;
+  } else {
+    AMC_CHECK_ARG(D.in_ch >= 1 && D.patch >= 1 && D.img_h >= D.patch && D.img_w >= D.patch, "bad ViT geometry");
+    AMC_CHECK_ARG(D.input_layout == AMC_INPUT_MODEL || (D.in_ch == 1 && (D.img_h * D.img_w) % 2 == 0),
+                  "raw interleaved input needs in_channels=1 and an even image");
+    m.Ttok = (D.img_h / D.patch) * (D.img_w / D.patch);
+    m.K = D.in_ch * D.patch * D.patch;
+    m.has_cls = 1;
+  }
+  m.T = m.Ttok + m.has_cls;
+  AMC_CHECK_ARG(m.T <= 288, "T=%d tokens per frame exceeds the single-CTA attention limit (288)", m.T);
+  if (D.dtype == AMC_BF16) {
+    AMC_CHECK_ARG(D.d % 8 == 0 && D.F % 8 == 0 && m.K % 8 == 0,
+                  "bf16 path needs d_model, ffn_hidden and the patch width (%d) to be multiples of 8", m.K);
+  }
+  if (D.p_drop > 0.f)
+    AMC_CHECK_ARG(D.d % 4 == 0 && D.F % 4 == 0, "dropout needs d_model and ffn_hidden multiples of 4");
+  m.M = (int64_t)m.B * m.T;
+  AMC_CHECK_ARG(m.M * (int64_t)std::max(3 * m.d, m.F) < (int64_t)1 << 40, "problem too large");
+  return 0;
+}
+
+inline int64_t up64(int64_t v) { return (v + 63) / 64 * 64; }
+
+int make_layout(const AmcDesc& D, const Dims& m, AmcParamLayout& L) {
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += up64(n); return r; };
+  const int64_t d = m.d, F = m.F;
+  L.emb_w = take(d * m.K);
+  L.emb_b = take(d);
+  L.cls = m.has_cls ? take(d) : -1;
+  L.layer0 = o;
+  int64_t lo = 0;
+  auto ltake = [&](int64_t n) { int64_t r = lo; lo += up64(n); return r; };
+  // q,k,v adjacent -> one [3d,d] matrix and one [3d] bias (d*d and d are padded only when not %64:
+  // adjacency must be exact, so these six are NOT individually padded)
+  L.wq = lo; L.wk = lo + d * d; L.wv = lo + 2 * d * d; lo = up64(lo + 3 * d * d);
+  L.bq = lo; L.bk = lo + d; L.bv = lo + 2 * d; lo = up64(lo + 3 * d);
+  L.wo = ltake(d * d); L.bo = ltake(d);
+  L.g1 = ltake(d); L.be1 = ltake(d);
+  L.w1 = ltake(F * d); L.b1 = ltake(F);
+  L.w2 = ltake(d * F); L.b2 = ltake(d);
+  L.g2 = ltake(d); L.be2 = ltake(d);
+  L.layer_stride = lo;
+  o += lo * m.L;
+  if (D.head_ln) { L.head_ln_w = take(d); L.head_ln_b = take(d); } else { L.head_ln_w = L.head_ln_b = -1; }
+  L.head_w = take((int64_t)m.C * d);
+  L.head_b = take(m.C);
+  L.total = o;
+  L.T = m.T; L.Ttok = m.Ttok; L.K_embed = m.K; L.pad_ = 0;
+  return 0;
+}
+
+// ---- workspace ----------------------------------------------------------------------------
+struct LayerBuf {
+  void *qkv, *o, *xhat1, *x1_16, *hid, *xhat2;
+  float *rstd1, *x1_32, *rstd2;
+};
+struct Work {
+  bf16* w16 = nullptr;   // bf16 copy of the parameter blob
+  bf16* wT = nullptr;    // per layer: wqkvT [d,3d] | woT [d,d] | w1T [d,F] | w2T [F,d]
+  int64_t wT_stride = 0;
+  void* Apatch = nullptr;
+  std::vector<void*> x16;     // L+1 (training) or 2 (inference, ping-pong)
+  std::vector<float*> x32;
+  std::vector<LayerBuf> lay;  // L (training) or 1
+  float *u32, *hl, *hxhat, *hrstd, *dhl;
+  // backward scratch
+  float *dy32, *dw32, *t32, *du32;
+  void *dw16, *da, *du16, *dO, *dqkv, *demb;
+  size_t bytes = 0;
+};
+
+template <typename E>
+void carve(const AmcDesc& D, const Dims& m, const AmcParamLayout& L, char* base, Work& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const bool bf = D.dtype == AMC_BF16;
+  const size_t M = (size_t)m.M, d = m.d, F = m.F, e = sizeof(E);
+  if (bf) {
+    w.w16 = (bf16*)take((size_t)L.total * 2);
+    if (D.training) {
+      w.wT_stride = (int64_t)(3 * d * d + d * d + 2 * d * F);
+      w.wT = (bf16*)take((size_t)w.wT_stride * m.L * 2);
+    }
+  }
+  w.Apatch = take((size_t)m.B * m.Ttok * m.K * e);
+  const int nx = D.training ? m.L + 1 : 2;
+  w.x16.resize(nx);
+  w.x32.resize(nx);
+  for (int i = 0; i < nx; ++i) {
+    w.x16[i] = take(M * d * e);
+    w.x32[i] = bf ? (float*)take(M * d * 4) : (float*)w.x16[i];
+  }
+  const int nl = D.training ? m.L : 1;
+  w.lay.resize(std::max(nl, 1));
+  for (int i = 0; i < (int)w.lay.size(); ++i) {
+    LayerBuf& b = w.lay[i];
+    b.qkv = take(M * 3 * d * e);
+    b.o = take(M * d * e);
+    b.x1_16 = take(M * d * e);
+    b.x1_32 = bf ? (float*)take(M * d * 4) : (float*)b.x1_16;
+    b.hid = take(M * F * e);
+    if (D.training) {
+      b.xhat1 = take(M * d * e);
+      b.xhat2 = take(M * d * e);
+      b.rstd1 = (float*)take(M * 4);
+      b.rstd2 = (float*)take(M * 4);
+    } else {
+      b.xhat1 = b.xhat2 = nullptr;
+      b.rstd1 = b.rstd2 = nullptr;
+    }
+  }
+  w.u32 = (float*)take(M * d * 4);
+  w.hl = (float*)take((size_t)m.B * d * 4);
+  w.hxhat = (float*)take((size_t)m.B * d * 4);
+  w.hrstd = (float*)take((size_t)m.B * 4);
+  w.dhl = (float*)take((size_t)m.B * d * 4);
+  if (D.training) {
+    w.dy32 = (float*)take(M * d * 4);
+    w.dw32 = (float*)take(M * d * 4);
+    w.t32 = (float*)take(M * d * 4);
+    w.du32 = (float*)take(M * d * 4);
+    w.dw16 = take(M * d * e);
+    w.da = take(M * F * e);
+    w.du16 = take(M * d * e);
+    w.dO = take(M * d * e);
+    w.dqkv = take(M * 3 * d * e);
+    w.demb = take((size_t)m.B * m.Ttok * d * e);
+  }
+  w.bytes = off;
+}
+
+template <typename E> int gemm(const GemmArgs& g, cudaStream_t st);
+template <> int gemm<float>(const GemmArgs& g, cudaStream_t st) { return gemm_f32(g, st); }
+template <> int gemm<bf16>(const GemmArgs& g, cudaStream_t st) { return gemm_bf16(g, st); }
+
+inline int pick_split_k(int Mo, int No, int K) {
+  const int tiles = ceil_div(Mo, 128) * ceil_div(No, 128);
+  int s = std::max(1, (148 * 2) / std::max(tiles, 1));
+  s = std::min(s, std::max(1, K / 256));
+  return s;
+}
+
+template <typename E>
+struct Model {
+  const AmcDesc& D;
+  Dims m;
+  AmcParamLayout L;
+  Work w;
+  const float* params;
+  cudaStream_t st;
+  DropoutCfg drop;
+
+  Model(const AmcDesc& D_, const float* params_, cudaStream_t st_) : D(D_), params(params_), st(st_) {}
+
+  int init(void* workspace) {
+    AMC_TRY(validate(D, m));
+    AMC_TRY(make_layout(D, m, L));
+    AMC_CHECK_ARG(workspace != nullptr || m.B == 0, "workspace is NULL");
+    AMC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    carve<E>(D, m, L, (char*)workspace, w);
+    drop = make_dropout(D.p_drop, D.seed, D.offset, true);
+    return 0;
+  }
+  // fp32 parameter inside the blob
+  const float* P(int64_t off) const { return params + off; }
+  const float* PL(int l, int64_t off) const { return params + L.layer0 + (int64_t)l * L.layer_stride + off; }
+  // GEMM-operand view of a weight matrix (element type E)
+  const E* WL(int l, int64_t off) const {
+    const int64_t o = L.layer0 + (int64_t)l * L.layer_stride + off;
+    if (sizeof(E) == 2) return reinterpret_cast<const E*>(w.w16 + o);
+    return reinterpret_cast<const E*>(params + o);
+  }
+  const E* Wemb() const {
+    if (sizeof(E) == 2) return reinterpret_cast<const E*>(w.w16 + L.emb_w);
+    return reinterpret_cast<const E*>(params + L.emb_w);
+  }
+  const LayerBuf& LB(int l) const { return w.lay[D.training ? l : 0]; }
+  int xi(int l) const { return D.training ? l : (l & 1); }
+
+  int pack_weights() {
+    if (sizeof(E) != 2) return 0;
+    AMC_TRY(cast_blob(L.total, params, w.w16, st));
+    if (!D.training) return 0;
+    const int64_t d = m.d, F = m.F;
+    TransposeBatch tb;
+    tb.n = 0;
+    for (int l = 0; l < m.L; ++l) {
+      bf16* t = w.wT + (int64_t)l * w.wT_stride;
+      tb.t[tb.n++] = {PL(l, L.wq), t, (int)(3 * d), (int)d, 0};                       // [3d,d] -> [d,3d]
+      tb.t[tb.n++] = {PL(l, L.wo), t + 3 * d * d, (int)d, (int)d, 0};                 // [d,d]  -> [d,d]
+      tb.t[tb.n++] = {PL(l, L.w1), t + 4 * d * d, (int)F, (int)d, 0};                 // [F,d]  -> [d,F]
+      tb.t[tb.n++] = {PL(l, L.w2), t + 4 * d * d + d * F, (int)d, (int)F, 0};         // [d,F]  -> [F,d]
+      if (tb.n == 8 || l == m.L - 1) {
+        AMC_TRY(transpose_batch(tb, st));
+        tb.n = 0;
+      }
+    }
+    return 0;
+  }
+
+  int frontend(const float* src, const float* pos) {
+    if (m.B == 0) return 0;
+    AMC_TRY(patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
+    GemmArgs g;
+    g.M = m.B * m.Ttok; g.N = m.d; g.K = m.K;
+    g.A = w.Apatch; g.lda = m.K;
+    g.B = Wemb(); g.ldb = m.K;
+    g.epi.bias = P(L.emb_b);
+    g.epi.pos = pos;
+    g.epi.map_Ttok = m.Ttok; g.epi.map_T = m.T; g.epi.map_cls = m.has_cls;
+    g.epi.drop = drop; g.epi.drop_site = site_pe();
+    g.epi.D16 = w.x16[0]; g.epi.ldd16 = m.d;
+    if (sizeof(E) == 2) { g.epi.D32 = w.x32[0]; g.epi.ldd32 = m.d; }
+    AMC_TRY(gemm<E>(g, st));
+    if (m.has_cls)
+      AMC_TRY(cls_rows<E>(m.B, m.T, m.d, P(L.cls), pos, (E*)w.x16[0], sizeof(E) == 2 ? w.x32[0] : nullptr, drop, st));
+    return 0;
+  }
+
+  int layer_fwd(int l) {
+    const int M = (int)m.M, d = m.d, F = m.F;
+    const LayerBuf& b = LB(l);
+    const int xin = xi(l), xout = xi(l + 1);
+    GemmArgs g;
+    // fused QKV projection: one [3d,d] weight (three state_dict tensors, adjacent) -- multi_head_attention.py:18
+    g = GemmArgs();
+    g.M = M; g.N = 3 * d; g.K = d; g.A = w.x16[xin]; g.lda = d; g.B = WL(l, L.wq); g.ldb = d;
+    g.epi.bias = PL(l, L.bq); g.epi.D16 = b.qkv; g.epi.ldd16 = 3 * d;
+    AMC_TRY(gemm<E>(g, st));
+    AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
+    // out-proj + dropout1 + residual -> u ; norm1 (encoder_layer.py:24-25)
+    g = GemmArgs();
+    g.M = M; g.N = d; g.K = d; g.A = b.o; g.lda = d; g.B = WL(l, L.wo); g.ldb = d;
+    g.epi.bias = PL(l, L.bo); g.epi.drop = drop; g.epi.drop_site = site_attn(l);
+    g.epi.res32 = w.x32[xin]; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
+    AMC_TRY(gemm<E>(g, st));
+    AMC_TRY(ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
+                      sizeof(E) == 2 ? b.x1_32 : nullptr, (E*)b.xhat1, b.rstd1, st));
+    // FFN (position_wise_feed_forward.py:12-17): linear1 + ReLU + dropout
+    g = GemmArgs();
+    g.M = M; g.N = F; g.K = d; g.A = b.x1_16; g.lda = d; g.B = WL(l, L.w1); g.ldb = d;
+    g.epi.bias = PL(l, L.b1); g.epi.relu = 1; g.epi.drop = drop; g.epi.drop_site = site_hidden(l);
+    g.epi.D16 = b.hid; g.epi.ldd16 = F;
+    AMC_TRY(gemm<E>(g, st));
+    // linear2 + dropout2 + residual -> u ; norm2 (encoder_layer.py:32-33)
+    g = GemmArgs();
+    g.M = M; g.N = d; g.K = F; g.A = b.hid; g.lda = F; g.B = WL(l, L.w2); g.ldb = F;
+    g.epi.bias = PL(l, L.b2); g.epi.drop = drop; g.epi.drop_site = site_ffn(l);
+    g.epi.res32 = b.x1_32; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
+    AMC_TRY(gemm<E>(g, st));
+    AMC_TRY(ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
+                      sizeof(E) == 2 ? w.x32[xout] : nullptr, (E*)b.xhat2, b.rstd2, st));
+    return 0;
+  }
+
+  int forward(const float* src, const float* pos, float* logits, float* enc_out) {
+    if (m.B == 0) return 0;
+    AMC_TRY(pack_weights());
+    AMC_TRY(frontend(src, pos));
+    for (int l = 0; l < m.L; ++l) AMC_TRY(layer_fwd(l));
+    const float* xL = w.x32[xi(m.L)];
+    if (enc_out)
+      AMC_CUDA(cudaMemcpyAsync(enc_out, xL, (size_t)m.M * m.d * 4, cudaMemcpyDeviceToDevice, st));
+    if (logits)
+      AMC_TRY(head_fwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, D.head_ln_eps, xL,
+                       D.head_ln ? P(L.head_ln_w) : nullptr, D.head_ln ? P(L.head_ln_b) : nullptr, P(L.head_w),
+                       P(L.head_b), logits, w.hl, w.hxhat, w.hrstd, st));
+    return 0;
+  }
+
+  // ---- backward ---------------------------------------------------------------------------
+  // weight-gradient GEMM: dW[No, Ki] += dY[M, No]^T X[M, Ki]
+  int wgrad(int No, int Ki, const void* dY, int ldy, const void* X, int ldx, float* dW) {
+    GemmArgs g;
+    g.M = No; g.N = Ki; g.K = (int)m.M;
+    g.A = dY; g.lda = ldy; g.transA = 1;
+    g.B = X; g.ldb = ldx; g.transB = 1;
+    g.split_k = pick_split_k(No, Ki, g.K);
+    g.epi.D32 = dW; g.epi.ldd32 = Ki; g.epi.accumulate = 1;
+    return gemm<E>(g, st);
+  }
+  // activation-gradient GEMM: dX[M, Ki] = dY[M, No] W[No, Ki]; the bf16 path reads the pre-transposed copy
+  void dgrad_operand(GemmArgs& g, int l, int64_t woff, int64_t wT_off, int No, int Ki) {
+    if (sizeof(E) == 2) {
+      g.B = w.wT + (int64_t)l * w.wT_stride + wT_off;  // [Ki, No]
+      g.ldb = No; g.transB = 0;
+    } else {
+      g.B = PL(l, woff);                                // [No, Ki] read as [K=No, N=Ki]
+      g.ldb = Ki; g.transB = 1;
+    }
+  }
+
+  int layer_bwd(int l, float* grads) {
+    const int M = (int)m.M, d = m.d, F = m.F;
+    const int64_t dd = (int64_t)d * d;
+    const LayerBuf& b = LB(l);
+    float* G = grads + L.layer0 + (int64_t)l * L.layer_stride;
+    GemmArgs g;
+    // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
+    AMC_TRY(ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
+                      G + L.be2, drop, site_ffn(l), st));
+    AMC_TRY(colsum<E>(M, d, (const E*)w.dw16, d, G + L.b2, st));
+    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2));
+    // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
+    g = GemmArgs();
+    g.M = M; g.N = F; g.K = d; g.A = w.dw16; g.lda = d;
+    dgrad_operand(g, l, L.w2, 4 * dd + (int64_t)d * F, d, F);
+    g.epi.mask_src = b.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
+    g.epi.D16 = w.da; g.epi.ldd16 = F;
+    AMC_TRY(gemm<E>(g, st));
+    AMC_TRY(colsum<E>(M, F, (const E*)w.da, F, G + L.b1, st));
+    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1));
+    // dgrad FFN1 + skip -> gradient w.r.t. x1
+    g = GemmArgs();
+    g.M = M; g.N = d; g.K = F; g.A = w.da; g.lda = F;
+    dgrad_operand(g, l, L.w1, 4 * dd, F, d);
+    g.epi.res32 = w.dw32; g.epi.ldres = d; g.epi.D32 = w.t32; g.epi.ldd32 = d;
+    AMC_TRY(gemm<E>(g, st));
+    // norm1 backward
+    AMC_TRY(ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
+                      G + L.be1, drop, site_attn(l), st));
+    AMC_TRY(colsum<E>(M, d, (const E*)w.du16, d, G + L.bo, st));
+    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo));
+    g = GemmArgs();
+    g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
+    dgrad_operand(g, l, L.wo, 3 * dd, d, d);
+    g.epi.D16 = w.dO; g.epi.ldd16 = d;
+    AMC_TRY(gemm<E>(g, st));
+    AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, st));
+    AMC_TRY(colsum<E>(M, 3 * d, (const E*)w.dqkv, 3 * d, G + L.bq, st));
+    AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq));
+    // dgrad QKV + skip -> gradient w.r.t. the layer input
+    g = GemmArgs();
+    g.M = M; g.N = d; g.K = 3 * d; g.A = w.dqkv; g.lda = 3 * d;
+    dgrad_operand(g, l, L.wq, 0, 3 * d, d);
+    g.epi.res32 = w.du32; g.epi.ldres = d; g.epi.D32 = w.dy32; g.epi.ldd32 = d;
+    AMC_TRY(gemm<E>(g, st));
+    return 0;
+  }
+
+  int backward(const float* dlogits, const float* denc_out, float* grads, int s0, int s1) {
+    AMC_CHECK_ARG(D.training, "amc_model_bwd needs a forward run with desc.training=1");
+    AMC_CHECK_ARG(0 <= s0 && s0 <= s1 && s1 <= m.L + 2, "bad stage range [%d,%d)", s0, s1);
+    if (m.B == 0) return 0;
+    const size_t nx = (size_t)m.M * m.d;
+    for (int s = s0; s < s1; ++s) {
+      if (s == 0) {
+        AMC_CHECK_ARG(dlogits || denc_out, "amc_model_bwd: dlogits and denc_out are both NULL");
+        if (dlogits) {
+          AMC_TRY(head_bwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, dlogits, P(L.head_w),
+                           D.head_ln ? P(L.head_ln_w) : nullptr, w.hl, w.hxhat, w.hrstd, w.dhl, w.dy32,
+                           grads + L.head_w, grads + L.head_b, D.head_ln ? grads + L.head_ln_w : nullptr,
+                           D.head_ln ? grads + L.head_ln_b : nullptr, st));
+          if (denc_out) {
+            add_inplace_kernel<<<148 * 4, 256, 0, st>>>(nx, w.dy32, denc_out);
+            AMC_LAUNCH_CHECK();
+          }
+        } else {
+          AMC_CUDA(cudaMemcpyAsync(w.dy32, denc_out, nx * 4, cudaMemcpyDeviceToDevice, st));
+        }
+      } else if (s <= m.L) {
+        AMC_TRY(layer_bwd(m.L - s, grads));
+      } else {
+        // embedding front end: dcls, dW_emb, db_emb (input never needs a gradient: Appendix B)
+        if (m.has_cls) AMC_TRY(cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
+        AMC_TRY(gather_tok_rows<E>(m.B, m.T, m.Ttok, m.d, m.has_cls, w.dy32, (E*)w.demb, drop, st));
+        const int Mt = m.B * m.Ttok;
+        AMC_TRY(colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
+        GemmArgs g;
+        g.M = m.d; g.N = m.K; g.K = Mt;
+        g.A = w.demb; g.lda = m.d; g.transA = 1;
+        g.B = w.Apatch; g.ldb = m.K; g.transB = 1;
+        g.split_k = pick_split_k(m.d, m.K, Mt);
+        g.epi.D32 = grads + L.emb_w; g.epi.ldd32 = m.K; g.epi.accumulate = 1;
+        AMC_TRY(gemm<E>(g, st));
+      }
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+}  // namespace amc
+
+using namespace amc;
+
+extern "C" {
+
+int amc_abi_version(void) { return AMC_ABI_VERSION; }
+const char* amc_last_error(void) { return g_err; }
+
+int amc_param_layout(const AmcDesc* desc, AmcParamLayout* out) {
+  AMC_CHECK_ARG(desc && out, "NULL argument");
+  Dims m;
+  AMC_TRY(validate(*desc, m));
+  return make_layout(*desc, m, *out);
+}
+
+int amc_model_workspace(const AmcDesc* desc, AmcWorkspaceInfo* out) {
+  AMC_CHECK_ARG(desc && out, "NULL argument");
+  Dims m;
+  AmcParamLayout L;
+  AMC_TRY(validate(*desc, m));
+  AMC_TRY(make_layout(*desc, m, L));
+  Work w;
+  if (desc->dtype == AMC_BF16) carve<bf16>(*desc, m, L, nullptr, w);
+  else carve<float>(*desc, m, L, nullptr, w);
+  out->bytes = std::max<size_t>(w.bytes, 256);
+  out->saved_bytes = out->bytes;
+  return 0;
+}
+
+int amc_model_fwd(const AmcDesc* desc, const float* src, const float* params, const float* pos, void* workspace,
+                  float* logits, float* enc_out, amc_stream_t stream) {
+  AMC_CHECK_ARG(desc && params && pos, "NULL argument");
+  AMC_CHECK_ARG(src || desc->B == 0, "src is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (desc->dtype == AMC_BF16) {
+    Model<bf16> mdl(*desc, params, st);
+    AMC_TRY(mdl.init(workspace));
+    return mdl.forward(src, pos, logits, enc_out);
+  }
+  Model<float> mdl(*desc, params, st);
+  AMC_TRY(mdl.init(workspace));
+  return mdl.forward(src, pos, logits, enc_out);
+}
+
+int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, void* workspace, const float* dlogits,
+                  const float* denc_out, float* grads, int stage_begin, int stage_end, amc_stream_t stream) {
+  (void)src;
+  AMC_CHECK_ARG(desc && params && grads, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (desc->dtype == AMC_BF16) {
+    Model<bf16> mdl(*desc, params, st);
+    AMC_TRY(mdl.init(workspace));
+    return mdl.backward(dlogits, denc_out, grads, stage_begin, stage_end);
+  }
+  Model<float> mdl(*desc, params, st);
+  AMC_TRY(mdl.init(workspace));
+  return mdl.backward(dlogits, denc_out, grads, stage_begin, stage_end);
+}
+
+int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float label_smoothing, float grad_scale,
+                float loss_scale, float* dlogits, float* stats, amc_stream_t stream) {
+  AMC_CHECK_ARG(B >= 0 && C >= 1 && logits && labels, "bad argument");
+  return ce_loss(B, C, logits, labels, label_smoothing, grad_scale, loss_scale, dlogits, stats, (cudaStream_t)stream);
+}
+
+int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                        int64_t step, float* norm_ws, amc_stream_t stream) {
+  AMC_CHECK_ARG(n >= 0 && params && grads && exp_avg && exp_avg_sq && norm_ws, "bad argument");
+  return adamw_clip(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale,
+                    step, norm_ws, (cudaStream_t)stream);
+}
+
+int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA, const void* B, int ldb, int transB,
+             const float* bias, const float* res32, int ldres, int relu, void* D16, int ldd16, float* D32, int ldd32,
+             int accumulate, amc_stream_t stream) {
+  AMC_CHECK_ARG(A && B && (D16 || D32), "NULL argument");
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.transA = transA; g.B = B; g.ldb = ldb; g.transB = transB;
+  g.epi.bias = bias; g.epi.res32 = res32; g.epi.ldres = ldres; g.epi.relu = relu;
+  g.epi.D16 = D16; g.epi.ldd16 = ldd16; g.epi.D32 = D32; g.epi.ldd32 = ldd32; g.epi.accumulate = accumulate;
+  if (accumulate && !bias && !res32 && !D16) g.split_k = pick_split_k(M, N, K);
+  if (dtype == AMC_BF16) return gemm_bf16(g, (cudaStream_t)stream);
+  AMC_CHECK_ARG(dtype == AMC_F32, "unknown dtype %d", dtype);
+  return gemm_f32(g, (cudaStream_t)stream);
+}
+
+int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream) {
+  AMC_CHECK_ARG(qkv && out, "NULL argument");
+  if (dtype == AMC_BF16) return attention_fwd<bf16>(B, T, h, dh, (const bf16*)qkv, (bf16*)out, (cudaStream_t)stream);
+  return attention_fwd<float>(B, T, h, dh, (const float*)qkv, (float*)out, (cudaStream_t)stream);
+}
+int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv,
+                      amc_stream_t stream) {
+  AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
+  if (dtype == AMC_BF16)
+    return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, (cudaStream_t)stream);
+  return attention_bwd<float>(B, T, h, dh, (const float*)qkv, (const float*)dout, (float*)dqkv, (cudaStream_t)stream);
+}
+
+int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamma, const float* beta, float eps,
+                      void* y16, float* y32, void* xhat, float* rstd, amc_stream_t stream) {
+  AMC_CHECK_ARG(u && gamma && beta, "NULL argument");
+  if (dtype == AMC_BF16)
+    return ln_fwd<bf16>(M, d, u, gamma, beta, eps, (bf16*)y16, y32, (bf16*)xhat, rstd, (cudaStream_t)stream);
+  return ln_fwd<float>(M, d, u, gamma, beta, eps, (float*)y16, y32, (float*)xhat, rstd, (cudaStream_t)stream);
+}
+int amc_layernorm_bwd(int dtype, int M, int d, const float* dy, const void* xhat, const float* rstd,
+                      const float* gamma, void* du16, float* du32, float* dgamma, float* dbeta, amc_stream_t stream) {
+  AMC_CHECK_ARG(dy && xhat && rstd && gamma, "NULL argument");
+  DropoutCfg nodrop = make_dropout(0.f, 0, 0, false);
+  if (dtype == AMC_BF16)
+    return ln_bwd<bf16>(M, d, dy, (const bf16*)xhat, rstd, gamma, (bf16*)du16, du32, dgamma, dbeta, nodrop, 0,
+                        (cudaStream_t)stream);
+  return ln_bwd<float>(M, d, dy, (const float*)xhat, rstd, gamma, (float*)du16, du32, dgamma, dbeta, nodrop, 0,
+                       (cudaStream_t)stream);
+}
+
+int amc_frontend_fwd(const AmcDesc* desc, const float* src, const float* emb_w, const float* emb_b, const float* cls,
+                     const float* pos, void* scratch, size_t scratch_bytes, float* x0, amc_stream_t stream) {
+  AMC_CHECK_ARG(desc && src && emb_w && emb_b && pos && x0, "NULL argument");
+  AMC_CHECK_ARG(desc->dtype == AMC_F32, "amc_frontend_fwd operator call is fp32-only; use amc_model_fwd for bf16");
+  Dims m;
+  AMC_TRY(validate(*desc, m));
+  AMC_CHECK_ARG(!m.has_cls || cls, "cls is NULL");
+  const size_t need = (size_t)m.B * m.Ttok * m.K * sizeof(float);
+  AMC_CHECK_ARG(scratch && scratch_bytes >= need, "scratch too small: need %zu bytes", need);
+  cudaStream_t st = (cudaStream_t)stream;
+  AMC_TRY(patchify<float>(*desc, m.Ttok, m.K, src, (float*)scratch, st));
+  GemmArgs g;
+  g.M = m.B * m.Ttok; g.N = m.d; g.K = m.K; g.A = scratch; g.lda = m.K; g.B = emb_w; g.ldb = m.K;
+  g.epi.bias = emb_b; g.epi.pos = pos; g.epi.map_Ttok = m.Ttok; g.epi.map_T = m.T; g.epi.map_cls = m.has_cls;
+  g.epi.D32 = x0; g.epi.ldd32 = m.d;
+  AMC_TRY(gemm_f32(g, st));
+  if (m.has_cls) {
+    DropoutCfg nodrop = make_dropout(0.f, 0, 0, false);
+    AMC_TRY(cls_rows<float>(m.B, m.T, m.d, cls, pos, x0, nullptr, nodrop, st));
+  }
+  return 0;
+}
+
+}  // extern "C"

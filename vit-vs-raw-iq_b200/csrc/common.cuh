@@ -1,0 +1,130 @@
+// Shared helpers for the sm_100a kernels: error plumbing, element types, warp reductions,
+// counter-based dropout RNG.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/amc_b200.h"
+
+namespace amc {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define AMC_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::amc::set_error(__VA_ARGS__);             \
+      return -1;                                 \
+    }                                            \
+  } while (0)
+#define AMC_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ::amc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                       __LINE__);                                                         \
+      return (int)e__;                                                                    \
+    }                                                                                     \
+  } while (0)
+#define AMC_LAUNCH_CHECK() AMC_CUDA(cudaGetLastError())
+#define AMC_TRY(expr)          \
+  do {                         \
+    int r__ = (expr);          \
+    if (r__ != 0) return r__;  \
+  } while (0)
+
+// ---- element helpers --------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename E> __device__ __forceinline__ E from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> float4 (16-byte fp32 load / 8-byte bf16 load)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const bf16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- dropout RNG ------------------------------------------------------------------------
+// Philox4x32-10 keyed by (seed), counter = (idx, site, offset).  One call yields the keep
+// decisions of 4 consecutive elements.  Stateless: backward regenerates the same masks from
+// (seed, offset, site, element index) instead of storing them.
+struct DropoutCfg {
+  float p;          // drop probability; 0 => disabled
+  float scale;      // 1/(1-p)
+  uint32_t thresh;  // keep iff rnd >= thresh, thresh = p * 2^32
+  uint32_t seed_lo, seed_hi;
+  uint32_t off_lo, off_hi;
+};
+inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool training) {
+  DropoutCfg c;
+  c.p = (training && p > 0.f) ? p : 0.f;
+  c.scale = c.p > 0.f ? 1.f / (1.f - c.p) : 1.f;
+  double t = (double)c.p * 4294967296.0;
+  c.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  c.seed_lo = (uint32_t)seed;
+  c.seed_hi = (uint32_t)(seed >> 32);
+  c.off_lo = (uint32_t)offset;
+  c.off_hi = (uint32_t)(offset >> 32);
+  return c;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// keep-multipliers (0 or scale) for elements [4*q4, 4*q4+4) of dropout site `site`
+__device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint32_t site, uint64_t q4) {
+  uint4 r = philox4x32_10(make_uint4((uint32_t)q4, (uint32_t)(q4 >> 32) ^ (site << 8), c.off_lo, c.off_hi),
+                          make_uint2(c.seed_lo, c.seed_hi));
+  return make_float4(r.x >= c.thresh ? c.scale : 0.f, r.y >= c.thresh ? c.scale : 0.f,
+                     r.z >= c.thresh ? c.scale : 0.f, r.w >= c.thresh ? c.scale : 0.f);
+}
+// dropout sites (layer l): 0 = after positional encoding (encoder.py:111);
+// 1+3l = after attention out-proj (encoder_layer.py:24); 2+3l = FFN hidden (position_wise_feed_forward.py:15);
+// 3+3l = after FFN (encoder_layer.py:32)
+__host__ __device__ __forceinline__ uint32_t site_pe() { return 0; }
+__host__ __device__ __forceinline__ uint32_t site_attn(int l) { return 1 + 3 * l; }
+__host__ __device__ __forceinline__ uint32_t site_hidden(int l) { return 2 + 3 * l; }
+__host__ __device__ __forceinline__ uint32_t site_ffn(int l) { return 3 + 3 * l; }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace amc
