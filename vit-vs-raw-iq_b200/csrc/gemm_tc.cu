@@ -1,8 +1,397 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05) for the AMC_BF16 path.
+//
+//   D[M,N] = A * B^T, fp32 accumulation in TMEM, fused epilogue (gemm_common.cuh).
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer   cp.async.bulk.tensor (128B-swizzled tiles) -> 4..6 stage smem ring
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) per k-step,
+//                              tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> fused
+//                              bias/ReLU/mask/dropout/residual -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1 -- with K as small as d_model=128..256 the epilogue is as long as the MMAs.
+//
+// Operand layouts
+//   MODE_K  (forward, dgrad): A [M,K] and B [N,K] row-major (K contiguous)  -> K-major UMMA operands
+//   MODE_MN (wgrad): A [K,M] and B [K,N] row-major (token-major activations) -> MN-major UMMA operands,
+//           split-K over the token dimension with fp32 atomics into the gradient.
+// TMA zero-fills out-of-bounds rows / columns, so M, N, K need no padding (row pitch % 16 B == 0).
+#include <cuda.h>
+
+#include <algorithm>
+#include <initializer_list>
+
 #include "gemm_common.cuh"
+
 namespace amc {
-int gemm_bf16(const GemmArgs&, cudaStream_t) {
-  set_error("bf16 tcgen05 GEMM not built yet");
-  return -2;
+namespace {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 64;         // one 128-byte swizzle atom of bf16 per row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors -------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle:
+//   [0,14) start address >> 4   [16,30) leading-dim byte offset >> 4   [32,46) stride-dim byte offset >> 4
+//   [46,48) version = 1         [61,64) layout type: 2 = SWIZZLE_128B
+// K-major operand : rows of 128 B (64 bf16 of K); 8-row groups 1024 B apart  -> SBO = 1024, LBO unused (1)
+// MN-major operand: rows of 128 B (64 bf16 of M/N) indexed by k; 8-k groups 1024 B apart -> SBO = 1024;
+//                   64-wide M/N groups are separate TMA boxes 8192 B apart           -> LBO = 8192
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;              // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  int vec_ok;
+};
+
+template <int BN, int MODE_MN>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB,
+                                                              const TcParams p, const Epi epi) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                                         ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile % p.splits, mn = tile / p.splits;
+        const int tn = mn % p.tiles_n, tm = mn / p.tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          unsigned char* sa = smem + stage * C::STAGE_BYTES;
+          unsigned char* sb = sa + C::A_BYTES;
+          mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
+          if (MODE_MN == 0) {
+            tma_load_2d(&mapA, full_bar + stage, sa, kb * BK, m0);       // box {64 k, 128 rows}
+            tma_load_2d(&mapB, full_bar + stage, sb, kb * BK, n0);       // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)                            // boxes {64 m, 64 tokens}
+              tma_load_2d(&mapA, full_bar + stage, sa + j * 8192, m0 + 64 * j, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&mapB, full_bar + stage, sb + j * 8192, n0 + 64 * j, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, MODE_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar + as, aphase ^ 1);      // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);        // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            uint64_t adesc, bdesc;
+            if (MODE_MN == 0) {
+              adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              bdesc = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            } else {
+              adesc = make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024);
+              bdesc = make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+            }
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);            // frees the smem stage when the MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + as);                 // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mn = tile / p.splits;
+      const int tn = mn % p.tiles_n, tm = mn / p.tiles_n;
+      const int m = tm * BM + quad * 32 + lane;
+      const int n0 = tn * BN;
+      mbar_wait(tfull_bar + as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;                    // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
+          epi_apply4<bf16>(epi, m, n0 + c + j, v, p.M, p.N, p.vec_ok != 0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AMC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    AMC_CHECK_ARG(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return 0;
+}
+
+// 2-D bf16 tensor [rows, cols] row-major with pitch ld (elements); box = {box_cols (<= 64), box_rows}
+int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc;
+  AMC_TRY(get_encode_fn(&enc));
+  AMC_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "bf16 GEMM operand must be 16-byte aligned");
+  AMC_CHECK_ARG(ld % 8 == 0, "bf16 GEMM operand pitch (%d elements) must be a multiple of 8", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AMC_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols,
+                ld);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int MODE_MN>
+int launch(const GemmArgs& g, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap mapA, mapB;
+  if (MODE_MN == 0) {
+    AMC_TRY(make_map(&mapA, g.A, g.M, g.K, g.lda, BK, BM));
+    AMC_TRY(make_map(&mapB, g.B, g.N, g.K, g.ldb, BK, BN));
+  } else {
+    AMC_TRY(make_map(&mapA, g.A, g.K, g.M, g.lda, 64, BK));
+    AMC_TRY(make_map(&mapB, g.B, g.K, g.N, g.ldb, 64, BK));
+  }
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.tiles_m = ceil_div(g.M, BM);
+  p.tiles_n = ceil_div(g.N, BN);
+  p.kb_total = ceil_div(g.K, BK);
+  int splits = std::max(1, std::min(g.split_k, p.kb_total));
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);
+  p.vec_ok = epi_vec_ok<bf16>(g.epi, g.N) ? 1 : 0;
+  const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
+  AMC_CHECK_ARG(tiles < (1ll << 30), "gemm_bf16: too many tiles");
+  const int grid = (int)std::min<long long>(tiles, num_sms());
+  auto kern = gemm_tc_kernel<BN, MODE_MN>;
+  AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapB, p, g.epi);
+  AMC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
+  AMC_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  AMC_CHECK_ARG(g.transA == g.transB, "gemm_bf16: operands must both be K-major (forward/dgrad) or both "
+                "token-major (wgrad); mixed layouts are not built");
+  AMC_CHECK_ARG(g.split_k == 1 || (g.epi.accumulate && !g.epi.bias && !g.epi.res32 && !g.epi.D16),
+                "gemm_bf16: split-K needs an accumulate-only epilogue");
+  AMC_CHECK_ARG(g.epi.drop.p == 0.f || g.N % 4 == 0, "gemm_bf16: dropout epilogue needs N %% 4 == 0");
+  // N tile: least padding, ties -> larger tile
+  int best = 256;
+  long long best_pad = (long long)ceil_div(g.N, 256) * 256;
+  for (int bn : {128, 64}) {
+    const long long pad = (long long)ceil_div(g.N, bn) * bn;
+    if (pad < best_pad) { best = bn; best_pad = pad; }
+  }
+  const int mn = g.transA ? 1 : 0;
+  if (best == 256) return mn ? launch<256, 1>(g, st) : launch<256, 0>(g, st);
+  if (best == 128) return mn ? launch<128, 1>(g, st) : launch<128, 0>(g, st);
+  return mn ? launch<64, 1>(g, st) : launch<64, 0>(g, st);
+}
+
 }  // namespace amc

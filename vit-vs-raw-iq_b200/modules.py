@@ -151,9 +151,8 @@ class _EncoderPathFn(torch.autograd.Function):
     routes gradients to them; the kernels read the flat blob they are views of."""
 
     @staticmethod
-    def forward(ctx, owner, src, want_logits, *params):
+    def forward(ctx, owner, src, want_logits, need_grad, *params):
         core = owner._core
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         desc = core.make_desc(src, training=need_grad, module_training=owner.training)
         B = desc.B
         dev = src.device
@@ -181,7 +180,7 @@ class _EncoderPathFn(torch.autograd.Function):
                                           core.n_layers + 2, stream), "amc_model_bwd")
         ctx.ws = None
         views = [grads[o:o + n].view(shape) for (o, n, shape) in core.slots]
-        return (None, None, None, *views)
+        return (None, None, None, None, *views)
 
 
 class _Core:
@@ -355,7 +354,9 @@ class _AMCBase(nn.Module):
         return self._core.flat
 
     def _run(self, src, want_logits):
-        return _EncoderPathFn.apply(self, src, want_logits, *self._core.params)
+        # grad mode is switched off inside Function.forward, so decide here whether to keep activations
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._core.params)
+        return _EncoderPathFn.apply(self, src, want_logits, need_grad, *self._core.params)
 
 
 class _EncoderBase(nn.Module):
