@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- IQ frames/s of the encoder hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W     # reference arm: CPU port of the reference path
+
+A "step" is one training step (zero_grad -> forward -> CE(label_smoothing) -> backward -> clip -> AdamW,
+R/training/train.py:258-271) over one batch of synthetic RadioML-shaped frames (random-init weights).
+Workload at N=1: BASELINE.json configs[1] = ViT, 32x64 IQ image, patch 16, d=256, 6 layers, bf16.
+  value : whole-job training frames/s with the input batches already resident in HBM
+  e2e   : same step driven from pinned HOST buffers: H2D of the raw dataset-layout frames + labels and a
+          D2H read of the loss every step are inside the timed region
+Both are timed with CUDA events, barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]; 19 classes / dropout 0.1 / lr 1e-4 / wd 1e-3 from V/training/train.py:59-93
+    "vit_p16_d256_L6": dict(kind="vit", batch=8192, lr=1e-4, wd=1e-3,
+                            kw=dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19,
+                                    d_model=256, n_head=8, n_layers=6, ffn_hidden=1024, drop_prob=0.1)),
+    # BASELINE.json configs[0] shape (R/training/train.py:84-95, 11 classes)
+    "rawiq_seg16_d128_L6": dict(kind="rawiq", batch=2048, lr=1e-4, wd=1e-4,
+                                kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8,
+                                        n_layers=6, ffn_hidden=1024, drop_prob=0.2, use_cls_token=True,
+                                        embedding_type="segment", segment_size=16)),
+    # production ViT (V/training/train.py:83-88)
+    "vit_p4_d128_L6": dict(kind="vit", batch=1024, lr=1e-4, wd=1e-3,
+                           kw=dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=4, num_classes=19,
+                                   d_model=128, n_head=8, n_layers=6, ffn_hidden=512, drop_prob=0.1)),
+}
+DEFAULT_WORKLOAD = "vit_p16_d256_L6"
+
+
+def geometry(w):
+    kw = w["kw"]
+    if w["kind"] == "vit":
+        ttok = (kw["img_size_h"] // kw["patch_size"]) * (kw["img_size_w"] // kw["patch_size"])
+        kemb = kw["in_channels"] * kw["patch_size"] ** 2
+        T = ttok + 1
+    else:
+        ttok = kw["seq_length"] // kw["segment_size"]
+        kemb = kw["in_channels"] * kw["segment_size"]
+        T = ttok + (1 if kw.get("use_cls_token", True) else 0)
+    return T, ttok, kemb
+
+
+def flops_per_frame(w):
+    """Algorithmic forward FLOPs per frame; training = 3x."""
+    kw = w["kw"]
+    T, ttok, kemb = geometry(w)
+    d, F, L, C = kw["d_model"], kw["ffn_hidden"], kw["n_layers"], kw["num_classes"]
+    return L * T * (8 * d * d + 4 * d * F + 4 * T * d) + 2 * ttok * kemb * d + 2 * d * C
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or
+                 k.startswith("nvmlClocksThrottleReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) == bit and bin(bit).count("1") == 1:
+                        short = name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+                        if short not in ("GpuIdle", "None", "All"):
+                            self.reasons.add(short)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the numpy oracle (a port of the reference's algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_train_frames_per_s(w, sample_frames, steps, warmup):
+    import numpy as np
+    from oracle import amc_oracle as O
+    kw = {k: v for k, v in w["kw"].items() if k != "drop_prob"}
+    cfg = O.Config(kind=w["kind"], **kw)
+    params = O.init_params(cfg, 0)
+    rng = np.random.default_rng(0)
+    shape = (sample_frames, 1, 32, 64) if w["kind"] == "vit" else (sample_frames, 2, kw["seq_length"])
+    src = rng.standard_normal(shape).astype(np.float32)
+    labels = rng.integers(0, cfg.num_classes, sample_frames)
+    pk = [k for k in params if k not in O.BUFFER_KEYS]
+    m = {k: np.zeros_like(params[k]) for k in pk}
+    v = {k: np.zeros_like(params[k]) for k in pk}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, g = O.loss_and_grads(src, labels, params, cfg, 0.1)
+        _, g = O.clip_grad_norm(g, 1.0)
+        p2, m, v = O.adamw_step(params, g, m, v, it + 1, w["lr"], (0.9, 0.99), 1e-8, w["wd"])
+        params.update(p2)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sample_frames * len(times) / sum(times), sum(times) / len(times)
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        import numpy  # noqa: F401
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    fps, sec = cpu_port_train_frames_per_s(w, sample, args.steps, max(args.warmup, 1))
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "frames_per_step": sample, "note":
+                   "CPU numpy port (oracle/) of the reference train step, dropout omitted (favours the CPU arm)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} train steps of {sample} frames, numpy/BLAS on {cores} threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: workload's)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=256, help="frames per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w, args.workload)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import vit_vs_raw_iq_b200 as amc
+    from vit_vs_raw_iq_b200 import _lib, synth
+    from vit_vs_raw_iq_b200.trainer import HostPipeline, TrainStep, predict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or w["batch"]
+    kw = dict(w["kw"])
+    T, ttok, kemb = geometry(w)
+
+    torch.manual_seed(0)
+    cls = amc.ViTAMCTransformer if w["kind"] == "vit" else amc.RawIQAMCTransformer
+    model = cls(**kw, device=dev, compute_dtype=args.dtype)
+    classes = synth.CLASSES_19 if kw["num_classes"] == 19 else synth.CLASSES_11
+
+    # synthetic dataset-layout frames [n, 1024, 2]; a small pool is tiled to the batch (content does not
+    # change the arithmetic; a 64 MB batch is far larger than... the activations it produces are >> L2)
+    pool_n = 2048
+    X, y, _ = synth.make_frames(pool_n, classes=classes, seed=42 + rank)
+    stats = synth.normalization_stats(X)
+    model.set_raw_input(stats)
+    n_batches = 3
+    reps = (B + pool_n - 1) // pool_n
+    host_x, host_y = [], []
+    for i in range(n_batches):
+        perm = np.random.default_rng(100 + i + 10 * rank).permutation(pool_n * reps)[:B] % pool_n
+        host_x.append(torch.from_numpy(X[perm]).pin_memory())
+        host_y.append(torch.from_numpy(y[perm]).pin_memory())
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    trainer = TrainStep(model, lr=w["lr"], weight_decay=w["wd"], betas=(0.9, 0.99), max_norm=1.0,
+                        label_smoothing=0.1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- device-resident training throughput (value) ------------------------------------------------
+    for i in range(args.warmup):
+        trainer.step(dev_x[i % n_batches], dev_y[i % n_batches])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.lib.amc_launch_count()
+    ms_train = timed(lambda i: trainer.step(dev_x[i % n_batches], dev_y[i % n_batches]), args.steps)
+    launches = _lib.lib.amc_launch_count() - launches0
+    loss, acc = trainer.read_stats()
+
+    # ---- end to end from host buffers (e2e) -----------------------------------------------------------
+    pipe = HostPipeline(trainer, tuple(host_x[0].shape))
+    for i in range(3):
+        pipe.step(host_x[i % n_batches], host_y[i % n_batches])
+    ms_e2e = timed(lambda i: pipe.step(host_x[i % n_batches], host_y[i % n_batches]), args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- inference (R/training/utils.py:311-320) -------------------------------------------------------
+    preds = torch.empty(B, dtype=torch.int64, device=dev)
+    for i in range(3):
+        predict(model, dev_x[i % n_batches], preds)
+    ms_inf = timed(lambda i: predict(model, dev_x[i % n_batches], preds), args.steps)
+    pred_host = torch.empty(B, dtype=torch.int64).pin_memory()
+
+    def infer_host(i):
+        xd = host_x[i % n_batches].to(dev, non_blocking=True)
+        predict(model, xd, preds)
+        pred_host.copy_(preds, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for i in range(2):
+        infer_host(i)
+    ms_inf_e2e = timed(infer_host, args.steps)
+
+    # ---- in-situ kernel-class timing for the roofline --------------------------------------------------
+    _lib.profile(True)
+    prof_steps = 3
+    for i in range(prof_steps):
+        trainer.step(dev_x[i % n_batches], dev_y[i % n_batches])
+    prof = _lib.profile_dump()
+    _lib.profile(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    fl_frame = flops_per_frame(w)
+    frames = B * world
+    train_fps = frames * args.steps / (ms_train / 1e3)
+    gemm = {k: v for k, v in prof.items() if k.startswith("gemm")}
+    g_ms = sum(v["ms"] for v in gemm.values())
+    g_fl = sum(v["flops"] for v in gemm.values())
+    g_by = sum(v["bytes"] for v in gemm.values())
+    g_n = sum(v["n"] for v in gemm.values())
+    tot_ms = sum(v["ms"] for v in prof.values())
+    achieved_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {
+        "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all call sites)" if args.dtype == "bf16" else
+                  "gemm_simt_kernel (fp32 FMA GEMM)",
+        "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+        "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+        "launches_per_step": g_n / prof_steps, "avg_launch_ms": g_ms / max(g_n, 1),
+        "share_of_step": g_ms / tot_ms if tot_ms else None,
+        "hbm_view": {"algorithmic_GBps": g_by / (g_ms * 1e-3) / 1e9 if g_ms else 0.0, "peak": peaks["hbm_gbs"],
+                     "frac": (g_by / (g_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if g_ms else 0.0},
+    }
+    classes_ms = {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    line = {
+        "metric": "train_frames_per_sec", "value": train_fps, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "global_batch": frames, "tokens": T,
+                   **{k: kw[k] for k in ("d_model", "n_head", "n_layers", "ffn_hidden", "num_classes", "drop_prob")},
+                   "parallelism": f"dp{world}", "optimizer": "clip1.0+AdamW", "label_smoothing": 0.1,
+                   "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; 3 batches rotate",
+                   "input": "raw [B,1024,2] fp32 frames, z-score+framing fused in the front end"},
+        "model_tflops": train_fps * 3 * fl_frame / 1e12,
+        "model_tflops_frac_of_bf16_peak": train_fps * 3 * fl_frame / 1e12 / (peaks["tf_sustained"] * world),
+        "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "infer": {"value": frames * args.steps / (ms_inf / 1e3), "unit": "frames/s",
+                  "e2e_value": frames * args.steps / (ms_inf_e2e / 1e3),
+                  "e2e_h2d_bytes_per_step": host_x[0].numel() * 4, "e2e_d2h_bytes_per_step": B * 8},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "kernel_ms_per_step": classes_ms,
+        "train_loss": loss, "train_acc": acc,
+    }
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        fps, sec = cpu_port_train_frames_per_s(w, args.cpu_sample, 2, 1)
+        n_steps = max(2, min(40, int(12.0 / max(sec, 1e-3))))
+        fps, sec = cpu_port_train_frames_per_s(w, args.cpu_sample, n_steps, 1)
+        cores = host_threads()
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_steps} train steps of {args.cpu_sample} frames (numpy oracle port, "
+                                          f"no dropout), {time.perf_counter() - t0:.0f} s total"}
+    print(json.dumps(line), flush=True)
+    if args.profile_out:
+        with open(args.profile_out, "w") as f:
+            json.dump({"prof_steps": prof_steps, "classes": prof, "line": line}, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

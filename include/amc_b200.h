@@ -177,6 +177,14 @@ int amc_frontend_fwd(const AmcDesc* desc, const float* src, const float* emb_w, 
                      const float* cls, const float* pos, void* scratch, size_t scratch_bytes, float* x0,
                      amc_stream_t stream);
 
+/* ---- in-situ kernel timing (measurement only) ------------------------------------------
+ * When enabled, every launch site inside the library is bracketed by CUDA events on the launch
+ * stream.  amc_profile_dump synchronises the device and writes one line per kernel class:
+ *   "<class> <launches> <total_ms> <algorithmic_flops> <algorithmic_bytes>\n", then clears the records. */
+long long amc_launch_count(void);   /* kernels launched by the library so far (this process) */
+int amc_profile_enable(int on);
+int amc_profile_dump(char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,171 @@
+"""GPU tests of the fused training step (TrainStep), dropout consistency and the host pipeline."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN_CASES, GOLDEN_HP, load_golden  # noqa: E402
+
+import vit_vs_raw_iq_b200 as amc  # noqa: E402
+from vit_vs_raw_iq_b200.trainer import HostPipeline, TrainStep, predict  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def build(name, dtype, drop=0.0):
+    kind, kw = GOLDEN_CASES[name]
+    cls = amc.RawIQAMCTransformer if kind == "rawiq" else amc.ViTAMCTransformer
+    return cls(**kw, drop_prob=drop, device=DEV, compute_dtype=dtype)
+
+
+@pytest.mark.parametrize("name", ["rawiq_seg16", "rawiq_meanpool", "vit_p4", "vit_p16"])
+def test_fused_train_step_matches_reference_step(name):
+    """TrainStep.step (CE + backward + clip + AdamW, no autograd) == the reference's step on the golden case."""
+    z, params, grads, after = load_golden(name)
+    model = build(name, "fp32")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    ts = TrainStep(model, lr=GOLDEN_HP["lr"], weight_decay=GOLDEN_HP["weight_decay"], betas=GOLDEN_HP["betas"],
+                   max_norm=GOLDEN_HP["clip"], label_smoothing=GOLDEN_HP["label_smoothing"])
+    src = torch.from_numpy(z["src"]).to(DEV)
+    labels = torch.from_numpy(z["labels"]).to(DEV)
+    ts.step(src, labels)
+    loss, acc = ts.read_stats()
+    assert abs(loss - float(z["loss"])) < 1e-4
+    ref_acc = float((z["logits"].argmax(1) == z["labels"]).mean())
+    assert abs(acc - ref_acc) < 1e-6
+    assert abs(ts.norm_ws[1].item() - float(z["grad_norm"])) / float(z["grad_norm"]) < 1e-4
+    core = model._core
+    for n, p in model.named_parameters():
+        if n.endswith("w_k.bias"):
+            continue
+        upd = p.detach().cpu().numpy() - params[n]
+        ref_upd = after[n] - params[n]
+        assert np.abs(upd - ref_upd).max() < 1e-5 + 2e-2 * np.abs(ref_upd).max(), n
+    # flat gradient blob holds the same gradients as the reference
+    for (o, cnt, shape), p, (n, _) in zip(core.slots, core.params, model.named_parameters()):
+        pass
+    names = {id(p): n for n, p in model.named_parameters()}
+    for p, (o, cnt, shape) in zip(core.params, core.slots):
+        n = names[id(p)]
+        if n.endswith("w_k.bias"):
+            continue
+        g = ts.grads[o:o + cnt].view(shape).cpu().numpy()
+        r = grads[n]
+        assert np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-20) < 1e-3, n
+
+
+def test_dropout_backward_uses_the_forward_masks():
+    """With p>0 the masks are regenerated in backward from (seed, offset): the analytic directional
+    derivative must match a central finite difference taken with the *same* masks."""
+    torch.manual_seed(0)
+    model = amc.RawIQAMCTransformer(in_channels=2, seq_length=128, num_classes=11, d_model=32, n_head=4, n_layers=2,
+                                    ffn_hidden=64, drop_prob=0.3, device=DEV, segment_size=16, compute_dtype="fp32")
+    model.train()
+    core = model._core
+    src = torch.randn(6, 2, 128, device=DEV)
+    wgt = torch.randn(6, 11, device=DEV)
+
+    def f():
+        core.calls = 7          # freeze the dropout counter -> identical masks on every call
+        return (model(src) * wgt).sum()
+
+    out1 = f()
+    out2 = f()
+    assert torch.equal(out1, out2)
+    model.zero_grad()
+    out1.backward()
+    flat = model.flat_parameters()
+    g = torch.cat([p.grad.reshape(-1) for p in core.params])
+    v = torch.randn_like(g)
+    v /= v.norm()
+    analytic = float((g * v).sum())
+    eps = 3e-3
+    saved = [p.detach().clone() for p in core.params]
+    with torch.no_grad():
+        def shift(sign):
+            o = 0
+            for p, s in zip(core.params, saved):
+                p.copy_(s + sign * eps * v[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        shift(+1)
+        fp = float(f())
+        shift(-1)
+        fm = float(f())
+        shift(0)
+    numeric = (fp - fm) / (2 * eps)
+    assert abs(analytic - numeric) < 3e-2 * max(abs(analytic), abs(numeric), 1e-3), (analytic, numeric)
+    # dropout really is active in train mode and off in eval mode
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(src), model(src)
+    assert torch.equal(e1, e2)
+    model.train()
+    with torch.no_grad():
+        t1, t2 = model(src), model(src)          # counter advances -> different masks
+    assert not torch.equal(t1, t2)
+    assert (t1 - e1).abs().max() > 1e-3
+
+
+def test_dropout_keep_rate_and_scaling():
+    """E[dropout(x)] = x: averaging many train-mode encoder embeddings approaches the eval-mode one."""
+    torch.manual_seed(1)
+    model = amc.ViTAMCTransformer(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19,
+                                  d_model=64, n_head=4, n_layers=0, ffn_hidden=128, drop_prob=0.25, device=DEV,
+                                  compute_dtype="fp32")
+    src = torch.randn(64, 1, 32, 64, device=DEV)
+    with torch.no_grad():
+        model.eval()
+        ref = model.encoder(src)
+        model.train()
+        one = model.encoder(src)
+        zero_frac = float((one == 0).float().mean())
+        acc = torch.zeros_like(ref)
+        n = 200
+        for _ in range(n):
+            acc += model.encoder(src)
+    assert abs(zero_frac - 0.25) < 0.02
+    kept = one != 0
+    assert torch.allclose(one[kept], ref[kept] / 0.75, rtol=1e-5, atol=1e-6)
+    err = ((acc / n - ref).abs().mean() / ref.abs().mean()).item()
+    assert err < 0.08
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_training_reduces_loss_on_synthetic_iq(dtype):
+    """A few hundred fused steps on synthetic modulated IQ must learn (loss falls, accuracy > chance)."""
+    from vit_vs_raw_iq_b200 import synth
+    torch.manual_seed(0)
+    X, y, _ = synth.make_frames(2048, classes=synth.CLASSES_11[:4], seed=3)
+    keep = np.ones(len(X), dtype=bool)
+    stats = synth.normalization_stats(X)
+    model = amc.RawIQAMCTransformer(in_channels=2, seq_length=1024, num_classes=4, d_model=64, n_head=4, n_layers=2,
+                                    ffn_hidden=128, drop_prob=0.1, device=DEV, segment_size=16, compute_dtype=dtype)
+    model.set_raw_input(stats)
+    ts = TrainStep(model, lr=2e-3, weight_decay=1e-4)
+    xd, yd = torch.from_numpy(X[keep]).to(DEV), torch.from_numpy(y[keep]).to(DEV)
+    losses = []
+    for it in range(150):
+        i = (it * 256) % (len(xd) - 256)
+        ts.step(xd[i:i + 256], yd[i:i + 256])
+        if it % 25 == 24:
+            losses.append(ts.read_stats()[0])
+    assert losses[-1] < losses[0] - 0.1, losses
+    pred = predict(model, xd[:1024])
+    acc = float((pred == yd[:1024]).float().mean())
+    assert acc > 0.4, acc     # chance = 0.25
+
+
+def test_host_pipeline_step():
+    z, params, _, _ = load_golden("vit_p16")
+    model = build("vit_p16", "fp32")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    ts = TrainStep(model, lr=1e-3, weight_decay=1e-2)
+    src = torch.from_numpy(z["src"]).pin_memory()
+    labels = torch.from_numpy(z["labels"]).pin_memory()
+    pipe = HostPipeline(ts, tuple(src.shape))
+    l0 = pipe.step(src, labels)
+    assert abs(l0 - float(z["loss"])) < 1e-4
+    for _ in range(5):
+        l1 = pipe.step(src, labels)
+    assert l1 < l0

@@ -52,6 +52,8 @@ def _load():
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     lib.amc_abi_version.restype = C.c_int
     lib.amc_last_error.restype = C.c_char_p
+    lib.amc_launch_count.restype = C.c_longlong
+    lib.amc_launch_count.argtypes = []
     sigs = {
         "amc_param_layout": [C.POINTER(AmcDesc), C.POINTER(AmcParamLayout)],
         "amc_model_workspace": [C.POINTER(AmcDesc), C.POINTER(AmcWorkspaceInfo)],
@@ -65,6 +67,8 @@ def _load():
         "amc_layernorm_fwd": [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp],
         "amc_layernorm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "amc_frontend_fwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp],
+        "amc_profile_enable": [i32],
+        "amc_profile_dump": [C.c_char_p, C.c_size_t],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -72,7 +76,7 @@ def _load():
         fn.restype = C.c_int
     if lib.amc_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.amc_abi_version()} != expected {ABI_VERSION}; rebuild")
-    return lib, sorted(sigs) + ["amc_abi_version", "amc_last_error"]
+    return lib, sorted(sigs) + ["amc_abi_version", "amc_last_error", "amc_launch_count"]
 
 
 lib, EXPORTS = _load()
@@ -102,3 +106,18 @@ def workspace_bytes(desc: AmcDesc) -> int:
     out = AmcWorkspaceInfo()
     check(lib.amc_model_workspace(C.byref(desc), C.byref(out)), "amc_model_workspace")
     return int(out.bytes)
+
+
+def profile(enable: bool) -> None:
+    check(lib.amc_profile_enable(1 if enable else 0), "amc_profile_enable")
+
+
+def profile_dump() -> dict:
+    """{class: dict(n=launches, ms=total_ms, flops=..., bytes=...)} since the last dump (synchronises)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.amc_profile_dump(buf, len(buf)), "amc_profile_dump")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, fl, by = line.split()
+        out[name] = dict(n=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out

@@ -6,10 +6,12 @@
 
 #include "attention.cuh"
 #include "gemm_common.cuh"
+#include "profile.cuh"
 #include "rowops.cuh"
 
 namespace amc {
 
+long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,6 +21,12 @@ void set_error(const char* fmt, ...) {
 }
 
 namespace {
+
+#define AMC_PROF(name, flops, bytes, expr)      \
+  do {                                        \
+    ProfScope ps__(name, st, flops, bytes);   \
+    AMC_TRY(expr);                            \
+  } while (0)
 
 __global__ void add_inplace_kernel(size_t n, float* __restrict__ a, const float* __restrict__ b) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -186,9 +194,23 @@ void carve(const AmcDesc& D, const Dims& m, const AmcParamLayout& L, char* base,
   w.bytes = off;
 }
 
-template <typename E> int gemm(const GemmArgs& g, cudaStream_t st);
-template <> int gemm<float>(const GemmArgs& g, cudaStream_t st) { return gemm_f32(g, st); }
-template <> int gemm<bf16>(const GemmArgs& g, cudaStream_t st) { return gemm_bf16(g, st); }
+// algorithmic traffic of one GEMM call: operands once, outputs once, residual / mask once
+template <typename E> double gemm_bytes(const GemmArgs& g) {
+  const double e = sizeof(E), MN = (double)g.M * g.N;
+  double b = ((double)g.M * g.K + (double)g.N * g.K) * e;
+  if (g.epi.D16) b += MN * e;
+  if (g.epi.D32) b += MN * 4 * (g.epi.accumulate ? 2 : 1);
+  if (g.epi.res32) b += MN * 4;
+  if (g.epi.mask_src) b += MN * e;
+  return b;
+}
+template <typename E> int gemm_impl(const GemmArgs& g, cudaStream_t st);
+template <> int gemm_impl<float>(const GemmArgs& g, cudaStream_t st) { return gemm_f32(g, st); }
+template <> int gemm_impl<bf16>(const GemmArgs& g, cudaStream_t st) { return gemm_bf16(g, st); }
+template <typename E> int gemm(const GemmArgs& g, cudaStream_t st) {
+  ProfScope ps(g.name, st, 2.0 * g.M * g.N * g.K, gemm_bytes<E>(g));
+  return gemm_impl<E>(g, st);
+}
 
 inline int pick_split_k(int Mo, int No, int K) {
   const int tiles = ceil_div(Mo, 128) * ceil_div(No, 128);
@@ -236,7 +258,7 @@ struct Model {
 
   int pack_weights() {
     if (sizeof(E) != 2) return 0;
-    AMC_TRY(cast_blob(L.total, params, w.w16, st));
+    AMC_PROF("pack_weights", 0.0, (double)L.total * 6, cast_blob(L.total, params, w.w16, st));
     if (!D.training) return 0;
     const int64_t d = m.d, F = m.F;
     TransposeBatch tb;
@@ -248,7 +270,7 @@ struct Model {
       tb.t[tb.n++] = {PL(l, L.w1), t + 4 * d * d, (int)F, (int)d, 0};                 // [F,d]  -> [d,F]
       tb.t[tb.n++] = {PL(l, L.w2), t + 4 * d * d + d * F, (int)d, (int)F, 0};         // [d,F]  -> [F,d]
       if (tb.n == 8 || l == m.L - 1) {
-        AMC_TRY(transpose_batch(tb, st));
+        AMC_PROF("pack_weights", 0.0, 0.0, transpose_batch(tb, st));
         tb.n = 0;
       }
     }
@@ -257,11 +279,12 @@ struct Model {
 
   int frontend(const float* src, const float* pos) {
     if (m.B == 0) return 0;
-    AMC_TRY(patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
+    AMC_PROF("patchify", 0.0, (double)m.B * m.Ttok * m.K * (4 + sizeof(E)), patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
     GemmArgs g;
     g.M = m.B * m.Ttok; g.N = m.d; g.K = m.K;
     g.A = w.Apatch; g.lda = m.K;
     g.B = Wemb(); g.ldb = m.K;
+    g.name = "gemm_embed";
     g.epi.bias = P(L.emb_b);
     g.epi.pos = pos;
     g.epi.map_Ttok = m.Ttok; g.epi.map_T = m.T; g.epi.map_cls = m.has_cls;
@@ -270,7 +293,7 @@ struct Model {
     if (sizeof(E) == 2) { g.epi.D32 = w.x32[0]; g.epi.ldd32 = m.d; }
     AMC_TRY(gemm<E>(g, st));
     if (m.has_cls)
-      AMC_TRY(cls_rows<E>(m.B, m.T, m.d, P(L.cls), pos, (E*)w.x16[0], sizeof(E) == 2 ? w.x32[0] : nullptr, drop, st));
+      AMC_PROF("cls_rows", 0.0, 0.0, cls_rows<E>(m.B, m.T, m.d, P(L.cls), pos, (E*)w.x16[0], sizeof(E) == 2 ? w.x32[0] : nullptr, drop, st));
     return 0;
   }
 
@@ -282,30 +305,37 @@ struct Model {
     // fused QKV projection: one [3d,d] weight (three state_dict tensors, adjacent) -- multi_head_attention.py:18
     g = GemmArgs();
     g.M = M; g.N = 3 * d; g.K = d; g.A = w.x16[xin]; g.lda = d; g.B = WL(l, L.wq); g.ldb = d;
+    g.name = "gemm_qkv";
     g.epi.bias = PL(l, L.bq); g.epi.D16 = b.qkv; g.epi.ldd16 = 3 * d;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
+    {
+      ProfScope ps("attn_fwd", st, 4.0 * m.M * m.T * d, (double)M * 4 * d * sizeof(E));
+      AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
+    }
     // out-proj + dropout1 + residual -> u ; norm1 (encoder_layer.py:24-25)
     g = GemmArgs();
     g.M = M; g.N = d; g.K = d; g.A = b.o; g.lda = d; g.B = WL(l, L.wo); g.ldb = d;
+    g.name = "gemm_outproj";
     g.epi.bias = PL(l, L.bo); g.epi.drop = drop; g.epi.drop_site = site_attn(l);
     g.epi.res32 = w.x32[xin]; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
+    AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
                       sizeof(E) == 2 ? b.x1_32 : nullptr, (E*)b.xhat1, b.rstd1, st));
     // FFN (position_wise_feed_forward.py:12-17): linear1 + ReLU + dropout
     g = GemmArgs();
     g.M = M; g.N = F; g.K = d; g.A = b.x1_16; g.lda = d; g.B = WL(l, L.w1); g.ldb = d;
+    g.name = "gemm_ffn1";
     g.epi.bias = PL(l, L.b1); g.epi.relu = 1; g.epi.drop = drop; g.epi.drop_site = site_hidden(l);
     g.epi.D16 = b.hid; g.epi.ldd16 = F;
     AMC_TRY(gemm<E>(g, st));
     // linear2 + dropout2 + residual -> u ; norm2 (encoder_layer.py:32-33)
     g = GemmArgs();
     g.M = M; g.N = d; g.K = F; g.A = b.hid; g.lda = F; g.B = WL(l, L.w2); g.ldb = F;
+    g.name = "gemm_ffn2";
     g.epi.bias = PL(l, L.b2); g.epi.drop = drop; g.epi.drop_site = site_ffn(l);
     g.epi.res32 = b.x1_32; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
+    AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
                       sizeof(E) == 2 ? w.x32[xout] : nullptr, (E*)b.xhat2, b.rstd2, st));
     return 0;
   }
@@ -319,7 +349,7 @@ struct Model {
     if (enc_out)
       AMC_CUDA(cudaMemcpyAsync(enc_out, xL, (size_t)m.M * m.d * 4, cudaMemcpyDeviceToDevice, st));
     if (logits)
-      AMC_TRY(head_fwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, D.head_ln_eps, xL,
+      AMC_PROF("head", 0.0, 0.0, head_fwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, D.head_ln_eps, xL,
                        D.head_ln ? P(L.head_ln_w) : nullptr, D.head_ln ? P(L.head_ln_b) : nullptr, P(L.head_w),
                        P(L.head_b), logits, w.hl, w.hxhat, w.hrstd, st));
     return 0;
@@ -333,6 +363,7 @@ struct Model {
     g.A = dY; g.lda = ldy; g.transA = 1;
     g.B = X; g.ldb = ldx; g.transB = 1;
     g.split_k = pick_split_k(No, Ki, g.K);
+    g.name = "gemm_wgrad";
     g.epi.D32 = dW; g.epi.ldd32 = Ki; g.epi.accumulate = 1;
     return gemm<E>(g, st);
   }
@@ -354,42 +385,49 @@ struct Model {
     float* G = grads + L.layer0 + (int64_t)l * L.layer_stride;
     GemmArgs g;
     // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
-    AMC_TRY(ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
+    AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
                       G + L.be2, drop, site_ffn(l), st));
-    AMC_TRY(colsum<E>(M, d, (const E*)w.dw16, d, G + L.b2, st));
+    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, d, (const E*)w.dw16, d, G + L.b2, st));
     AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2));
     // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
     g = GemmArgs();
     g.M = M; g.N = F; g.K = d; g.A = w.dw16; g.lda = d;
     dgrad_operand(g, l, L.w2, 4 * dd + (int64_t)d * F, d, F);
+    g.name = "gemm_dgrad_ffn2";
     g.epi.mask_src = b.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
     g.epi.D16 = w.da; g.epi.ldd16 = F;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(colsum<E>(M, F, (const E*)w.da, F, G + L.b1, st));
+    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, F, (const E*)w.da, F, G + L.b1, st));
     AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1));
     // dgrad FFN1 + skip -> gradient w.r.t. x1
     g = GemmArgs();
     g.M = M; g.N = d; g.K = F; g.A = w.da; g.lda = F;
     dgrad_operand(g, l, L.w1, 4 * dd, F, d);
+    g.name = "gemm_dgrad_ffn1";
     g.epi.res32 = w.dw32; g.epi.ldres = d; g.epi.D32 = w.t32; g.epi.ldd32 = d;
     AMC_TRY(gemm<E>(g, st));
     // norm1 backward
-    AMC_TRY(ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
+    AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
                       G + L.be1, drop, site_attn(l), st));
-    AMC_TRY(colsum<E>(M, d, (const E*)w.du16, d, G + L.bo, st));
+    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, d, (const E*)w.du16, d, G + L.bo, st));
     AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo));
     g = GemmArgs();
     g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
     dgrad_operand(g, l, L.wo, 3 * dd, d, d);
+    g.name = "gemm_dgrad_outproj";
     g.epi.D16 = w.dO; g.epi.ldd16 = d;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, st));
-    AMC_TRY(colsum<E>(M, 3 * d, (const E*)w.dqkv, 3 * d, G + L.bq, st));
+    {
+      ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
+      AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, st));
+    }
+    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, 3 * d, (const E*)w.dqkv, 3 * d, G + L.bq, st));
     AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq));
     // dgrad QKV + skip -> gradient w.r.t. the layer input
     g = GemmArgs();
     g.M = M; g.N = d; g.K = 3 * d; g.A = w.dqkv; g.lda = 3 * d;
     dgrad_operand(g, l, L.wq, 0, 3 * d, d);
+    g.name = "gemm_dgrad_qkv";
     g.epi.res32 = w.du32; g.epi.ldres = d; g.epi.D32 = w.dy32; g.epi.ldd32 = d;
     AMC_TRY(gemm<E>(g, st));
     return 0;
@@ -404,7 +442,7 @@ struct Model {
       if (s == 0) {
         AMC_CHECK_ARG(dlogits || denc_out, "amc_model_bwd: dlogits and denc_out are both NULL");
         if (dlogits) {
-          AMC_TRY(head_bwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, dlogits, P(L.head_w),
+          AMC_PROF("head", 0.0, 0.0, head_bwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, dlogits, P(L.head_w),
                            D.head_ln ? P(L.head_ln_w) : nullptr, w.hl, w.hxhat, w.hrstd, w.dhl, w.dy32,
                            grads + L.head_w, grads + L.head_b, D.head_ln ? grads + L.head_ln_w : nullptr,
                            D.head_ln ? grads + L.head_ln_b : nullptr, st));
@@ -419,15 +457,16 @@ struct Model {
         AMC_TRY(layer_bwd(m.L - s, grads));
       } else {
         // embedding front end: dcls, dW_emb, db_emb (input never needs a gradient: Appendix B)
-        if (m.has_cls) AMC_TRY(cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
-        AMC_TRY(gather_tok_rows<E>(m.B, m.T, m.Ttok, m.d, m.has_cls, w.dy32, (E*)w.demb, drop, st));
+        if (m.has_cls) AMC_PROF("frontend_bwd_misc", 0.0, 0.0, cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
+        AMC_PROF("frontend_bwd_misc", 0.0, 0.0, gather_tok_rows<E>(m.B, m.T, m.Ttok, m.d, m.has_cls, w.dy32, (E*)w.demb, drop, st));
         const int Mt = m.B * m.Ttok;
-        AMC_TRY(colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
+        AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
         GemmArgs g;
         g.M = m.d; g.N = m.K; g.K = Mt;
         g.A = w.demb; g.lda = m.d; g.transA = 1;
         g.B = w.Apatch; g.ldb = m.K; g.transB = 1;
         g.split_k = pick_split_k(m.d, m.K, Mt);
+        g.name = "gemm_wgrad";
         g.epi.D32 = grads + L.emb_w; g.epi.ldd32 = m.K; g.epi.accumulate = 1;
         AMC_TRY(gemm<E>(g, st));
       }
@@ -444,6 +483,7 @@ using namespace amc;
 extern "C" {
 
 int amc_abi_version(void) { return AMC_ABI_VERSION; }
+long long amc_launch_count(void) { return g_launch_count; }
 const char* amc_last_error(void) { return g_err; }
 
 int amc_param_layout(const AmcDesc* desc, AmcParamLayout* out) {
@@ -500,6 +540,7 @@ int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, vo
 int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float label_smoothing, float grad_scale,
                 float loss_scale, float* dlogits, float* stats, amc_stream_t stream) {
   AMC_CHECK_ARG(B >= 0 && C >= 1 && logits && labels, "bad argument");
+  ProfScope ps("ce_loss", (cudaStream_t)stream);
   return ce_loss(B, C, logits, labels, label_smoothing, grad_scale, loss_scale, dlogits, stats, (cudaStream_t)stream);
 }
 
@@ -507,6 +548,7 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
                         float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                         int64_t step, float* norm_ws, amc_stream_t stream) {
   AMC_CHECK_ARG(n >= 0 && params && grads && exp_avg && exp_avg_sq && norm_ws, "bad argument");
+  ProfScope ps("adamw_clip", (cudaStream_t)stream, 0.0, (double)n * 32);
   return adamw_clip(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale,
                     step, norm_ws, (cudaStream_t)stream);
 }

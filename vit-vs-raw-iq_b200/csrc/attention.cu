@@ -211,6 +211,209 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(int T, int h, int dh, con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Small-sequence variant (T <= 32 tokens, head dim <= 32, e.g. ViT patch 16: T = 9): one THREAD per
+// (frame, head, query row); a CTA packs as many (frame, head) pairs as fit so all lanes work.
+// Q/K/V (and dO) of the CTA's pairs are staged in shared memory as fp32 with coalesced vector loads;
+// results go back through the same tiles so global stores are coalesced too.
+// ---------------------------------------------------------------------------------------------
+template <typename E>
+__device__ __forceinline__ void small_load(float* dst, int stride, const E* __restrict__ src, int ld, int rows, int dh,
+                                           int tid, int nthreads) {
+  const int q = dh >> 2;
+  for (int i = tid; i < rows * q; i += nthreads) {
+    const int r = i / q, c = (i - r * q) * 4;
+    const float4 v = load4(src + (size_t)r * ld + c);
+    float* o = dst + r * stride + c;
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+}
+template <typename E>
+__device__ __forceinline__ void small_store(E* __restrict__ dst, int ld, const float* src, int stride, int rows, int dh,
+                                            int tid, int nthreads) {
+  const int q = dh >> 2;
+  for (int i = tid; i < rows * q; i += nthreads) {
+    const int r = i / q, c = (i - r * q) * 4;
+    const float* o = src + r * stride + c;
+    store4(dst + (size_t)r * ld + c, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+template <typename E, int MAXT>
+__global__ void __launch_bounds__(256) attn_small_fwd_kernel(int npairs, int T, int h, int dh, int ppc,
+                                                             const E* __restrict__ qkv, E* __restrict__ out,
+                                                             float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  const int d = h * dh, ld = 3 * d, stride = dh + 1, tile = T * stride;
+  const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int p = 0; p < np; ++p) {
+    const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
+    const E* base = qkv + (size_t)b * T * ld + hh * dh;
+    float* Q = sm + p * 3 * tile;
+    small_load(Q, stride, base, ld, T, dh, tid, nt);
+    small_load(Q + tile, stride, base + d, ld, T, dh, tid, nt);
+    small_load(Q + 2 * tile, stride, base + 2 * d, ld, T, dh, tid, nt);
+  }
+  __syncthreads();
+  const int p = tid / T, i = tid - p * T;
+  if (p < np) {
+    float* Q = sm + p * 3 * tile;
+    const float* K = Q + tile;
+    const float* V = Q + 2 * tile;
+    float* q = Q + i * stride;
+    float s[MAXT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      float a = -INFINITY;
+      if (j < T) {
+        a = 0.f;
+        for (int c = 0; c < dh; ++c) a = fmaf(q[c], K[j * stride + c], a);
+        a *= scale;
+      }
+      s[j] = a;
+      mx = fmaxf(mx, a);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      s[j] = j < T ? __expf(s[j] - mx) : 0.f;
+      l += s[j];
+    }
+    const float inv = 1.f / l;
+    for (int c = 0; c < dh; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j)
+        if (j < T) a = fmaf(s[j], V[j * stride + c], a);
+      q[c] = a * inv;                       // own q row is dead: reuse it as the output staging row
+    }
+  }
+  __syncthreads();
+  for (int pp = 0; pp < np; ++pp) {
+    const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
+    small_store(out + (size_t)b * T * d + hh * dh, d, sm + pp * 3 * tile, stride, T, dh, tid, nt);
+  }
+}
+
+template <typename E, int MAXT>
+__global__ void __launch_bounds__(256) attn_small_bwd_kernel(int npairs, int T, int h, int dh, int ppc,
+                                                             const E* __restrict__ qkv, const E* __restrict__ dout,
+                                                             E* __restrict__ dqkv, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  const int d = h * dh, ld = 3 * d, stride = dh + 1, tile = T * stride, pt = T * (T + 1);
+  const int per_pair = 4 * tile + 2 * pt;
+  const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int p = 0; p < np; ++p) {
+    const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
+    const E* base = qkv + (size_t)b * T * ld + hh * dh;
+    float* Q = sm + p * per_pair;
+    small_load(Q, stride, base, ld, T, dh, tid, nt);
+    small_load(Q + tile, stride, base + d, ld, T, dh, tid, nt);
+    small_load(Q + 2 * tile, stride, base + 2 * d, ld, T, dh, tid, nt);
+    small_load(Q + 3 * tile, stride, dout + (size_t)b * T * d + hh * dh, d, T, dh, tid, nt);
+  }
+  __syncthreads();
+  const int p = tid / T, i = tid - p * T;
+  const bool act = p < np;
+  float* Q = sm + (act ? p : 0) * per_pair;
+  float* K = Q + tile;
+  float* V = Q + 2 * tile;
+  float* dO = Q + 3 * tile;
+  float* P = Q + 4 * tile;
+  float* dS = P + pt;
+  if (act) {   // phase 1: row i of P and dS
+    const float* q = Q + i * stride;
+    const float* o = dO + i * stride;
+    float s[MAXT], dp[MAXT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      float a = -INFINITY, g = 0.f;
+      if (j < T) {
+        a = 0.f;
+        for (int c = 0; c < dh; ++c) {
+          a = fmaf(q[c], K[j * stride + c], a);
+          g = fmaf(o[c], V[j * stride + c], g);
+        }
+        a *= scale;
+      }
+      s[j] = a;
+      dp[j] = g;
+      mx = fmaxf(mx, a);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      s[j] = j < T ? __expf(s[j] - mx) : 0.f;
+      l += s[j];
+    }
+    const float inv = 1.f / l;
+    float dl = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      s[j] *= inv;
+      dl = fmaf(s[j], dp[j], dl);
+    }
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j)
+      if (j < T) {
+        P[i * (T + 1) + j] = s[j];
+        dS[i * (T + 1) + j] = s[j] * (dp[j] - dl) * scale;
+      }
+  }
+  __syncthreads();
+  float dq[32], dk[32], dv[32];
+  if (act) {   // phase 2: dQ_i (as query row i) and dK_i, dV_i (as key row i)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { dq[c] = 0.f; dk[c] = 0.f; dv[c] = 0.f; }
+    for (int j = 0; j < T; ++j) {
+      const float ds_ij = dS[i * (T + 1) + j];     // query i, key j
+      const float ds_ji = dS[j * (T + 1) + i];     // query j, key i
+      const float p_ji = P[j * (T + 1) + i];
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < dh) {
+          dq[c] = fmaf(ds_ij, K[j * stride + c], dq[c]);
+          dk[c] = fmaf(ds_ji, Q[j * stride + c], dk[c]);
+          dv[c] = fmaf(p_ji, dO[j * stride + c], dv[c]);
+        }
+    }
+  }
+  __syncthreads();   // every read of Q/K/V/dO is done: reuse the tiles as output staging
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < dh) {
+        Q[i * stride + c] = dq[c];
+        K[i * stride + c] = dk[c];
+        V[i * stride + c] = dv[c];
+      }
+  }
+  __syncthreads();
+  for (int pp = 0; pp < np; ++pp) {
+    const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
+    E* base = dqkv + (size_t)b * T * ld + hh * dh;
+    const float* S = sm + pp * per_pair;
+    small_store(base, ld, S, stride, T, dh, tid, nt);
+    small_store(base + d, ld, S + tile, stride, T, dh, tid, nt);
+    small_store(base + 2 * d, ld, S + 2 * tile, stride, T, dh, tid, nt);
+  }
+}
+
+inline bool use_small(int T, int dh) { return T <= 32 && dh <= 32 && dh % 4 == 0; }
+// pairs per CTA: fill <= 256 threads and <= ~72 KB of shared memory (3 CTAs per SM)
+inline int small_ppc(int T, size_t bytes_per_pair) {
+  int ppc = std::max(1, 256 / T);
+  ppc = std::min<int>(ppc, std::max<size_t>(1, (72 * 1024) / bytes_per_pair));
+  return ppc;
+}
+
 inline int pick_warps(int T) { return std::max(1, std::min(8, (T + 7) / 8)); }
 
 }  // namespace
@@ -220,6 +423,23 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
+  if (use_small(T, dh)) {
+    const size_t per_pair = (size_t)3 * T * (dh + 1) * sizeof(float);
+    const int ppc = small_ppc(T, per_pair), npairs = B * h;
+    const size_t sm = per_pair * ppc;
+    const int threads = ((ppc * T + 31) / 32) * 32;
+    if (T <= 16) {
+      if (sm > 48 * 1024)
+        AMC_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attn_small_fwd_kernel<E, 16><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, out, 1.f / sqrtf((float)dh));
+    } else {
+      if (sm > 48 * 1024)
+        AMC_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attn_small_fwd_kernel<E, 32><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, out, 1.f / sqrtf((float)dh));
+    }
+    AMC_LAUNCH_CHECK();
+    return 0;
+  }
   const int nw = pick_warps(T), stride = dh + SmemPad<E>::v;
   const int tile = (T * stride + 1) & ~1;
   const size_t smem = (size_t)2 * tile * sizeof(E) + (size_t)nw * (dh + T) * sizeof(float);
@@ -238,6 +458,23 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
+  if (use_small(T, dh)) {
+    const size_t per_pair = ((size_t)4 * T * (dh + 1) + 2 * T * (T + 1)) * sizeof(float);
+    const int ppc = small_ppc(T, per_pair), npairs = B * h;
+    const size_t sm = per_pair * ppc;
+    const int threads = ((ppc * T + 31) / 32) * 32;
+    if (T <= 16) {
+      if (sm > 48 * 1024)
+        AMC_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attn_small_bwd_kernel<E, 16><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, dout, dqkv, 1.f / sqrtf((float)dh));
+    } else {
+      if (sm > 48 * 1024)
+        AMC_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attn_small_bwd_kernel<E, 32><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, dout, dqkv, 1.f / sqrtf((float)dh));
+    }
+    AMC_LAUNCH_CHECK();
+    return 0;
+  }
   const int nw = pick_warps(T), stride = dh + SmemPad<E>::v;
   const int tile = (T * stride + 1) & ~1;
   size_t smem = (size_t)4 * tile * sizeof(E) + (size_t)(3 * T + 2 * nw * T) * sizeof(float);

@@ -31,7 +31,12 @@ void set_error(const char* fmt, ...);
       return (int)e__;                                                                    \
     }                                                                                     \
   } while (0)
-#define AMC_LAUNCH_CHECK() AMC_CUDA(cudaGetLastError())
+extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
+#define AMC_LAUNCH_CHECK()          \
+  do {                              \
+    ++::amc::g_launch_count;        \
+    AMC_CUDA(cudaGetLastError());   \
+  } while (0)
 #define AMC_TRY(expr)          \
   do {                         \
     int r__ = (expr);          \
@@ -75,7 +80,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- dropout RNG ------------------------------------------------------------------------
-// Philox4x32-10 keyed by (seed), counter = (idx, site, offset).  One call yields the keep
+// Counter-based hash keyed by (seed, offset, site) over the element index.  One call yields the keep
 // decisions of 4 consecutive elements.  Stateless: backward regenerates the same masks from
 // (seed, offset, site, element index) instead of storing them.
 struct DropoutCfg {
@@ -97,24 +102,22 @@ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool tra
   c.off_hi = (uint32_t)(offset >> 32);
   return c;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
+// 64-bit counter hash (splitmix64 finaliser): 64 random bits per group of 4 elements, 16 bits each.
+// Cheap enough (~4 integer instructions per element) to sit in a GEMM epilogue that must keep up with
+// tcgen05; dropout only needs an unbiased, well-mixed keep decision per element.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
 // keep-multipliers (0 or scale) for elements [4*q4, 4*q4+4) of dropout site `site`
 __device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint32_t site, uint64_t q4) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)q4, (uint32_t)(q4 >> 32) ^ (site << 8), c.off_lo, c.off_hi),
-                          make_uint2(c.seed_lo, c.seed_hi));
-  return make_float4(r.x >= c.thresh ? c.scale : 0.f, r.y >= c.thresh ? c.scale : 0.f,
-                     r.z >= c.thresh ? c.scale : 0.f, r.w >= c.thresh ? c.scale : 0.f);
+  const uint64_t key = ((uint64_t)c.seed_hi << 32 | c.seed_lo) ^ (((uint64_t)c.off_hi << 32 | c.off_lo) * 0x9E3779B97F4A7C15ull) ^
+                       ((uint64_t)site << 56);
+  const uint64_t r = mix64(mix64(q4 + key) ^ key);
+  const uint32_t t16 = c.thresh >> 16;
+  return make_float4((uint32_t)(r & 0xFFFF) >= t16 ? c.scale : 0.f, (uint32_t)((r >> 16) & 0xFFFF) >= t16 ? c.scale : 0.f,
+                     (uint32_t)((r >> 32) & 0xFFFF) >= t16 ? c.scale : 0.f, (uint32_t)(r >> 48) >= t16 ? c.scale : 0.f);
 }
 // dropout sites (layer l): 0 = after positional encoding (encoder.py:111);
 // 1+3l = after attention out-proj (encoder_layer.py:24); 2+3l = FFN hidden (position_wise_feed_forward.py:15);

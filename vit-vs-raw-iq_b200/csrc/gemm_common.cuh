@@ -26,82 +26,80 @@ struct Epi {
   int accumulate = 0;             // D32 += (atomic)
 };
 
+// ---- fast path: whole float4 in bounds, every pointer vector-aligned; registers only -------------
 template <typename E>
-__device__ __forceinline__ void epi_apply4(const Epi& e, int m, int n, float4 v, int M, int N, bool vec_ok) {
-  if (m >= M || n >= N) return;
-  const bool full = vec_ok && (n + 3 < N);
-  float a[4] = {v.x, v.y, v.z, v.w};
-  const int nv = full ? 4 : min(4, N - n);
+__device__ __forceinline__ void epi_fast4(const Epi& e, int m, int n, float4 v, int N) {
   if (e.bias) {
-    if (full) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-      a[0] += b.x; a[1] += b.y; a[2] += b.z; a[3] += b.w;
-    } else {
-      for (int j = 0; j < nv; ++j) a[j] += __ldg(e.bias + n + j);
-    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if (e.relu) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = fmaxf(a[j], 0.f);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
   if (e.mask_src) {
-    const E* mp = reinterpret_cast<const E*>(e.mask_src) + (size_t)m * e.ldmask + n;
-    if (full) {
-      float4 h = load4(mp);
-      a[0] = h.x > 0.f ? a[0] * e.mask_scale : 0.f;
-      a[1] = h.y > 0.f ? a[1] * e.mask_scale : 0.f;
-      a[2] = h.z > 0.f ? a[2] * e.mask_scale : 0.f;
-      a[3] = h.w > 0.f ? a[3] * e.mask_scale : 0.f;
-    } else {
-      for (int j = 0; j < nv; ++j) a[j] = to_f(mp[j]) > 0.f ? a[j] * e.mask_scale : 0.f;
-    }
+    const float4 h = load4(reinterpret_cast<const E*>(e.mask_src) + (size_t)m * e.ldmask + n);
+    const float s = e.mask_scale;
+    v.x = h.x > 0.f ? v.x * s : 0.f; v.y = h.y > 0.f ? v.y * s : 0.f;
+    v.z = h.z > 0.f ? v.z * s : 0.f; v.w = h.w > 0.f ? v.w * s : 0.f;
   }
   int orow = m;
   if (e.map_Ttok > 0) {
     const int b = m / e.map_Ttok, t = m - b * e.map_Ttok + e.map_cls;
     orow = b * e.map_T + t;
     if (e.pos) {
-      const float* pp = e.pos + (size_t)t * N + n;
-      if (full) {
-        float4 q = __ldg(reinterpret_cast<const float4*>(pp));
-        a[0] += q.x; a[1] += q.y; a[2] += q.z; a[3] += q.w;
-      } else {
-        for (int j = 0; j < nv; ++j) a[j] += __ldg(pp + j);
-      }
+      const float4 q = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)t * N + n));
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
   }
   if (e.drop.p > 0.f) {
-    // element index = orow * N + n ; N % 4 == 0 is required for dropout (checked on the host)
-    float4 k = dropout_mult4(e.drop, e.drop_site, ((uint64_t)orow * (uint64_t)N + (uint64_t)n) >> 2);
-    a[0] *= k.x; a[1] *= k.y; a[2] *= k.z; a[3] *= k.w;
+    const float4 k = dropout_mult4(e.drop, e.drop_site, ((uint64_t)orow * (uint64_t)N + (uint64_t)n) >> 2);
+    v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
   }
   if (e.res32) {
-    const float* rp = e.res32 + (size_t)orow * e.ldres + n;
-    if (full) {
-      float4 r = *reinterpret_cast<const float4*>(rp);
-      a[0] += r.x; a[1] += r.y; a[2] += r.z; a[3] += r.w;
-    } else {
-      for (int j = 0; j < nv; ++j) a[j] += rp[j];
-    }
+    const float4 r = *reinterpret_cast<const float4*>(e.res32 + (size_t)orow * e.ldres + n);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
   if (e.D32) {
     float* dp = e.D32 + (size_t)orow * e.ldd32 + n;
     if (e.accumulate) {
-      for (int j = 0; j < nv; ++j) atomicAdd(dp + j, a[j]);
-    } else if (full) {
-      *reinterpret_cast<float4*>(dp) = make_float4(a[0], a[1], a[2], a[3]);
+      atomicAdd(reinterpret_cast<float4*>(dp), v);     // red.global.add.v4.f32 (sm_90+)
     } else {
-      for (int j = 0; j < nv; ++j) dp[j] = a[j];
+      *reinterpret_cast<float4*>(dp) = v;
     }
   }
-  if (e.D16) {
-    E* dp = reinterpret_cast<E*>(e.D16) + (size_t)orow * e.ldd16 + n;
-    if (full) {
-      store4(dp, make_float4(a[0], a[1], a[2], a[3]));
-    } else {
-      for (int j = 0; j < nv; ++j) dp[j] = from_f<E>(a[j]);
+  if (e.D16) store4(reinterpret_cast<E*>(e.D16) + (size_t)orow * e.ldd16 + n, v);
+}
+
+// ---- slow path: ragged right edge or unaligned pointers; element-wise, kept out of line ---------
+template <typename E>
+__device__ __noinline__ void epi_slow4(const Epi& e, int m, int n, float4 v, int N) {
+  const float in[4] = {v.x, v.y, v.z, v.w};
+  const int b = e.map_Ttok > 0 ? m / e.map_Ttok : 0;
+  const int t = e.map_Ttok > 0 ? m - b * e.map_Ttok + e.map_cls : 0;
+  const int orow = e.map_Ttok > 0 ? b * e.map_T + t : m;
+  for (int j = 0; j < 4 && n + j < N; ++j) {
+    float a = in[j];
+    const int c = n + j;
+    if (e.bias) a += __ldg(e.bias + c);
+    if (e.relu) a = fmaxf(a, 0.f);
+    if (e.mask_src)
+      a = to_f(reinterpret_cast<const E*>(e.mask_src)[(size_t)m * e.ldmask + c]) > 0.f ? a * e.mask_scale : 0.f;
+    if (e.map_Ttok > 0 && e.pos) a += __ldg(e.pos + (size_t)t * N + c);
+    if (e.res32) a += e.res32[(size_t)orow * e.ldres + c];
+    if (e.D32) {
+      float* dp = e.D32 + (size_t)orow * e.ldd32 + c;
+      if (e.accumulate) atomicAdd(dp, a);
+      else *dp = a;
     }
+    if (e.D16) reinterpret_cast<E*>(e.D16)[(size_t)orow * e.ldd16 + c] = from_f<E>(a);
   }
+}
+
+template <typename E>
+__device__ __forceinline__ void epi_apply4(const Epi& e, int m, int n, float4 v, int M, int N, bool vec_ok) {
+  if (m >= M || n >= N) return;
+  if (vec_ok && n + 3 < N) epi_fast4<E>(e, m, n, v, N);
+  else epi_slow4<E>(e, m, n, v, N);   // (dropout requires N % 4 == 0 and aligned pointers: host-checked)
 }
 
 // true when every pointer/ld the epilogue touches allows 16-byte (fp32) / 8-byte (bf16) vectors
@@ -116,6 +114,7 @@ inline bool epi_vec_ok(const Epi& e, int N) {
 }
 
 struct GemmArgs {
+  const char* name = "gemm";  // profiling class
   int M = 0, N = 0, K = 0;
   const void* A = nullptr;  // element type E
   int lda = 0;

@@ -68,7 +68,7 @@ __device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int tid, const 
 }
 
 template <int TA, int TB>
-__global__ void __launch_bounds__(NT) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+__global__ void __launch_bounds__(NT, 2) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                        const float* __restrict__ B, int ldb, int k_per_split,
                                                        bool vecA, bool vecB, bool vecE, Epi epi) {
   __shared__ __align__(16) float As[2][BK][BM + PAD];

@@ -2,12 +2,12 @@
 //
 //   D[M,N] = A * B^T, fp32 accumulation in TMEM, fused epilogue (gemm_common.cuh).
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer   cp.async.bulk.tensor (128B-swizzled tiles) -> 4..6 stage smem ring
 //   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) per k-step,
 //                              tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2..5  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> fused
-//                              bias/ReLU/mask/dropout/residual -> global
+//   warps 2..9  epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> smem transpose -> fused
+//                              bias/ReLU/mask/dropout/residual -> coalesced global stores
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1 -- with K as small as d_model=128..256 the epilogue is as long as the MMAs.
 //
@@ -29,8 +29,10 @@ namespace {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // one 128-byte swizzle atom of bf16 per row
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;
+constexpr int NEPI_WARPS = 8;     // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int NTHREADS = 64 + 32 * NEPI_WARPS;
 constexpr int EPI_WARP0 = 2;
+constexpr int STG_LD = 32;      // floats per staging row; 16-byte chunks are XOR-swizzled by (row & 7)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +113,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -------------------------------------------------------------------------------
@@ -142,7 +152,8 @@ template <int BN> struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = NEPI_WARPS * 32 * STG_LD * 4;   // per-epilogue-warp transpose tiles
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
 };
 
 struct TcParams {
@@ -164,6 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s, 1);
-      mbar_init(tempty_bar + s, 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar + s, NEPI_WARPS);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -263,23 +275,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
       const int tn = mn % p.tiles_n, tm = mn / p.tiles_n;
-      const int m = tm * BM + quad * 32 + lane;
+      const int m_base = tm * BM + quad * 32;
       const int n0 = tn * BN;
       mbar_wait(tfull_bar + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+      // TMEM gives each thread one accumulator ROW (32 columns per load).  Row-per-thread global
+      // accesses would touch 32 different rows per instruction, so each 32x32 chunk is transposed through
+      // a per-warp smem tile: afterwards 8 lanes cover 128 contiguous bytes of one row and every epilogue
+      // load (bias, residual, ReLU mask) and store is fully coalesced.
+      const uint32_t stg = smem_u32(stage_base + (warp - EPI_WARP0) * (32 * STG_LD));
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+      const int half = (warp - EPI_WARP0) >> 2;       // which half of the tile's columns this warp drains
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         if (n0 + c >= p.N) break;                    // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                       __uint_as_float(r[j + 3]));
-          epi_apply4<bf16>(epi, m, n0 + c + j, v, p.M, p.N, p.vec_ok != 0);
+        for (int j = 0; j < 32; j += 4)
+          sts128(stg + (uint32_t)(lane * STG_LD + (((j >> 2) ^ (lane & 7)) << 2)) * 4, r[j], r[j + 1], r[j + 2],
+                 r[j + 3]);
+        __syncwarp();
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub_r;
+          const float4 v = lds128(stg + (uint32_t)(rr * STG_LD + ((((lane & 7)) ^ (rr & 7)) << 2)) * 4);
+          epi_apply4<bf16>(epi, m_base + rr, n0 + c + sub_c, v, p.M, p.N, p.vec_ok != 0);
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

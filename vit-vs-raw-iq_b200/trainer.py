@@ -1,0 +1,169 @@
+"""The training step and the inference loop of the reference, fused around the flat blobs.
+
+``TrainStep.step`` is R/training/train.py:258-271 (zero_grad -> forward -> CrossEntropyLoss(label
+smoothing) -> backward -> clip_grad_norm_ -> AdamW.step) without the autograd round trip: gradients
+accumulate straight into one flat fp32 blob, the loss / accuracy counters stay on the device
+(the reference's two ``.item()`` calls per step, train.py:274-277, are what serialise it), and under
+data parallelism the flat gradient is all-reduced in per-stage buckets that overlap the rest of
+backward (NCCL over NVLink).  ``predict`` is the loop of R/training/utils.py:311-320.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .modules import _AMCBase, _DTYPES
+
+
+class TrainStep:
+    def __init__(self, model: _AMCBase, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.99),
+                 eps: float = 1e-8, max_norm: float = 1.0, label_smoothing: float = 0.1,
+                 process_group=None, layers_per_bucket: int = 2):
+        self.model = model
+        self.core = model._core
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.max_norm, self.ls = max_norm, label_smoothing
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        flat = model.flat_parameters()
+        if not flat.is_cuda:
+            raise RuntimeError("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.dev = flat.device
+        n = flat.numel()
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.exp_avg = torch.zeros_like(self.grads)
+        self.exp_avg_sq = torch.zeros_like(self.grads)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=self.dev)     # [sum loss, #correct]
+        self.norm_ws = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.step_count = 0
+        self.frames_seen = 0
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_key = None
+        self._logits = self._dlogits = None
+        self.buckets = self._make_buckets(layers_per_bucket)
+
+    # gradient buckets: (stage_begin, stage_end, blob_lo, blob_hi) in backward order
+    def _make_buckets(self, per: int) -> List[Tuple[int, int, int, int]]:
+        L, nl = self.core.layout, self.core.n_layers
+        head_lo = L.head_ln_w if L.head_ln_w >= 0 else L.head_w
+        out = []
+        s = 1
+        first = True
+        while s <= nl:
+            e = min(nl + 1, s + per)
+            lo = L.layer0 + (nl - (e - 1)) * L.layer_stride          # lowest layer index in this bucket
+            hi = L.layer0 + (nl - (s - 1)) * L.layer_stride
+            if first:                                                # head rides with the top layers
+                out.append((0, e, lo, hi))
+                out.append((-1, -1, head_lo, L.total))
+                first = False
+            else:
+                out.append((s, e, lo, hi))
+            s = e
+        if first:
+            out.append((0, 1, head_lo, L.total))
+        out.append((nl + 1, nl + 2, 0, L.layer0))
+        return out
+
+    def _buffers(self, B: int, desc):
+        key = (B, desc.dtype, desc.p_drop > 0)
+        if self._ws_key != key:
+            self._ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=self.dev)
+            self._logits = torch.empty((B, self.core.C), dtype=torch.float32, device=self.dev)
+            self._dlogits = torch.empty_like(self._logits)
+            self._ws_key = key
+        return self._ws, self._logits, self._dlogits
+
+    def step(self, src: torch.Tensor, labels: torch.Tensor) -> None:
+        """One optimisation step on device tensors; statistics accumulate in ``self.stats``."""
+        core = self.core
+        self.model.train()
+        desc = core.make_desc(src, training=True, module_training=True)
+        B = desc.B
+        ws, logits, dlogits = self._buffers(B, desc)
+        flat = self.model.flat_parameters()
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        lib = _lib.lib
+        self.grads.zero_()
+        _lib.check(lib.amc_model_fwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), core.pos_buffer().data_ptr(),
+                                     ws.data_ptr(), logits.data_ptr(), 0, st), "amc_model_fwd")
+        gb = B * self.world
+        _lib.check(lib.amc_ce_loss(B, core.C, logits.data_ptr(), labels.data_ptr(), self.ls, 1.0 / gb, 1.0,
+                                   dlogits.data_ptr(), self.stats.data_ptr(), st), "amc_ce_loss")
+        works = []
+        for (s0, s1, lo, hi) in self.buckets:
+            if s0 >= 0:
+                _lib.check(lib.amc_model_bwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), ws.data_ptr(),
+                                             dlogits.data_ptr(), 0, self.grads.data_ptr(), s0, s1, st),
+                           "amc_model_bwd")
+            if self.world > 1:
+                # NCCL runs on its own stream after the kernels enqueued so far; later stages overlap it
+                works.append(torch.distributed.all_reduce(self.grads[lo:hi], group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        self.step_count += 1
+        self.frames_seen += B
+        _lib.check(lib.amc_adamw_clip_step(flat.numel(), flat.data_ptr(), self.grads.data_ptr(),
+                                           self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.lr,
+                                           self.betas[0], self.betas[1], self.eps, self.wd, self.max_norm, 1.0,
+                                           self.step_count, self.norm_ws.data_ptr(), st), "amc_adamw_clip_step")
+
+    def read_stats(self, reset: bool = True) -> Tuple[float, float]:
+        """(mean loss per frame, accuracy) since the last reset -- one device->host read."""
+        s = self.stats.tolist()
+        n = max(self.frames_seen, 1)
+        if reset:
+            self.stats.zero_()
+            self.frames_seen = 0
+        return s[0] / n, s[1] / n
+
+
+class HostPipeline:
+    """End-to-end step from HOST buffers: pinned host frames -> (async H2D on a copy stream, double
+    buffered) -> TrainStep.step -> loss read back.  This is the call a user of the reference's loop makes
+    (train.py:254-277: .to(device, non_blocking=True) ... loss.item())."""
+
+    def __init__(self, trainer: TrainStep, src_shape, lag: int = 1):
+        self.t = trainer
+        dev = trainer.dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.bufs = [(torch.empty(src_shape, dtype=torch.float32, device=dev),
+                      torch.empty((src_shape[0],), dtype=torch.int64, device=dev)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.bufs[0][0].numel() * 4 + self.bufs[0][1].numel() * 8
+        self.d2h_bytes = 8
+        self.i = 0
+
+    def step(self, src_host: torch.Tensor, labels_host: torch.Tensor) -> float:
+        k = self.i & 1
+        xs, ys = self.bufs[k]
+        cur = torch.cuda.current_stream(self.t.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])          # previous user of this buffer is done
+            xs.copy_(src_host, non_blocking=True)
+            ys.copy_(labels_host, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        cur.wait_event(self.ready[k])
+        self.t.step(xs, ys)
+        self.free[k].record(cur)
+        self.loss_host.copy_(self.t.stats, non_blocking=True)
+        self.t.stats.zero_()
+        self.t.frames_seen = 0
+        self.i += 1
+        cur.synchronize()                                      # the reference reads loss.item() every step
+        return float(self.loss_host[0]) / xs.shape[0]
+
+
+@torch.no_grad()
+def predict(model: _AMCBase, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """argmax class per frame (R/training/utils.py:311-317: model.eval(); model(x).max(1))."""
+    model.eval()
+    logits = model(src)
+    return torch.argmax(logits, dim=1, out=out)
