@@ -154,6 +154,17 @@ int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA,
              int transB, const float* bias, const float* res32, int ldres, int relu, void* D16, int ldd16,
              float* D32, int ldd32, int accumulate, amc_stream_t stream);
 
+/* bf16 GEMM with the fused post-LN epilogue used by the encoder block (encoder_layer.py:24-25,32-33):
+ *   u = A B^T + bias + res32 ; y = gamma * (u - mean) / sqrt(var + eps) + beta over each row (N <= 256, N % 32 == 0)
+ *   y16 (bf16), y32 (fp32), xhat (bf16, nullable), rstd (fp32 [M], nullable). */
+int amc_gemm_ln(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                const float* res32, const float* gamma, const float* beta, float eps, void* y16, float* y32,
+                void* xhat, float* rstd, amc_stream_t stream);
+/* bf16 GEMM whose epilogue applies the ReLU(+dropout) backward mask taken from the stored hidden activations
+ * (position_wise_feed_forward.py:14-15 backward): D16 = (A B^T) * (mask > 0 ? mask_scale : 0). */
+int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const void* mask,
+                       float mask_scale, void* D16, amc_stream_t stream);
+
 /* softmax(q k^T / sqrt(dh)) v for every (frame, head); qkv is [B*T, 3d] (q | k | v column blocks,
  * head hh = columns hh*dh..), out is [B*T, d] with heads concatenated
  * (multi_head_attention.py:34-47 + scale_dot_product_attention.py:26-37; mask is always None). */

@@ -150,3 +150,46 @@ def test_layernorm_fwd_bwd(dt, M, d):
     assert relerr(y16.float(), ref.detach()) < tol
     assert relerr(du32, ud.grad) < tol
     assert relerr(dgamma, gd.grad) < tol and relerr(dbeta, bd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (333, 128, 1024), (4096, 256, 1024), (77, 64, 64), (513, 96, 128)])
+def test_gemm_fused_layernorm_epilogue(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g)
+    gamma = torch.randn(N, device=DEV, generator=g)
+    beta = torch.randn(N, device=DEV, generator=g)
+    y16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    xhat = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    y32 = torch.empty(M, N, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    _lib.check(_lib.lib.amc_gemm_ln(M, N, K, A.data_ptr(), K, B.data_ptr(), K, bias.data_ptr(), res.data_ptr(),
+                                    gamma.data_ptr(), beta.data_ptr(), 1e-12, y16.data_ptr(), y32.data_ptr(),
+                                    xhat.data_ptr(), rstd.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    u = A.double() @ B.double().t() + bias.double() + res.double()
+    mean = u.mean(-1, keepdim=True)
+    var = u.var(-1, unbiased=False, keepdim=True)
+    xh = (u - mean) / torch.sqrt(var + 1e-12)
+    ref = gamma.double() * xh + beta.double()
+    assert relerr(y32, ref) < 1e-4
+    assert relerr(y16.float(), ref) < 1e-2
+    assert relerr(xhat.float(), xh) < 1e-2
+    assert relerr(rstd, (1 / torch.sqrt(var + 1e-12)).squeeze(-1)) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 1024, 256), (300, 512, 128), (77, 64, 64)])
+def test_gemm_relu_mask_epilogue(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    B = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+    mask = torch.randn(M, N, device=DEV, generator=g).clamp_min(0).bfloat16()
+    D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    _lib.check(_lib.lib.amc_gemm_relu_mask(M, N, K, A.data_ptr(), K, B.data_ptr(), K, mask.data_ptr(), 1.25,
+                                           D.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().t()) * (mask.double() > 0) * 1.25
+    assert relerr(D.float(), ref) < 1e-2
+    assert torch.equal(D == 0, (mask <= 0) | (D == 0))

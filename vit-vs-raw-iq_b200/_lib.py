@@ -62,6 +62,8 @@ def _load():
         "amc_ce_loss": [i32, i32, vp, vp, f32, f32, f32, vp, vp, vp],
         "amc_adamw_clip_step": [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, i64, vp, vp],
         "amc_gemm": [i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, vp, i32, i32, vp],
+        "amc_gemm_ln": [i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
+        "amc_gemm_relu_mask": [i32, i32, i32, vp, i32, vp, i32, vp, f32, vp, vp],
         "amc_attention_fwd": [i32, i32, i32, i32, i32, vp, vp, vp],
         "amc_attention_bwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp],
         "amc_layernorm_fwd": [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp],

@@ -202,6 +202,7 @@ template <typename E> double gemm_bytes(const GemmArgs& g) {
   if (g.epi.D32) b += MN * 4 * (g.epi.accumulate ? 2 : 1);
   if (g.epi.res32) b += MN * 4;
   if (g.epi.mask_src) b += MN * e;
+  if (g.epi.ln_xhat) b += MN * e;
   return b;
 }
 template <typename E> int gemm_impl(const GemmArgs& g, cudaStream_t st);
@@ -254,6 +255,7 @@ struct Model {
     return reinterpret_cast<const E*>(params + L.emb_w);
   }
   const LayerBuf& LB(int l) const { return w.lay[D.training ? l : 0]; }
+  bool fuse_ln() const { return sizeof(E) == 2 && m.d % 32 == 0 && m.d <= 256; }
   int xi(int l) const { return D.training ? l : (l & 1); }
 
   int pack_weights() {
@@ -317,10 +319,19 @@ struct Model {
     g.M = M; g.N = d; g.K = d; g.A = b.o; g.lda = d; g.B = WL(l, L.wo); g.ldb = d;
     g.name = "gemm_outproj";
     g.epi.bias = PL(l, L.bo); g.epi.drop = drop; g.epi.drop_site = site_attn(l);
-    g.epi.res32 = w.x32[xin]; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
-    AMC_TRY(gemm<E>(g, st));
-    AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
-                      sizeof(E) == 2 ? b.x1_32 : nullptr, (E*)b.xhat1, b.rstd1, st));
+    g.epi.res32 = w.x32[xin]; g.epi.ldres = d;
+    if (fuse_ln()) {   // bias + dropout + residual + LayerNorm inside the GEMM epilogue (row-owned in TMEM)
+      g.name = "gemm_outproj_ln";
+      g.epi.ln_gamma = PL(l, L.g1); g.epi.ln_beta = PL(l, L.be1); g.epi.ln_eps = D.ln_eps;
+      g.epi.D16 = b.x1_16; g.epi.ldd16 = d; g.epi.D32 = b.x1_32; g.epi.ldd32 = d;
+      g.epi.ln_xhat = b.xhat1; g.epi.ln_rstd = b.rstd1;
+      AMC_TRY(gemm<E>(g, st));
+    } else {
+      g.epi.D32 = w.u32; g.epi.ldd32 = d;
+      AMC_TRY(gemm<E>(g, st));
+      AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
+                        sizeof(E) == 2 ? b.x1_32 : nullptr, (E*)b.xhat1, b.rstd1, st));
+    }
     // FFN (position_wise_feed_forward.py:12-17): linear1 + ReLU + dropout
     g = GemmArgs();
     g.M = M; g.N = F; g.K = d; g.A = b.x1_16; g.lda = d; g.B = WL(l, L.w1); g.ldb = d;
@@ -333,10 +344,19 @@ struct Model {
     g.M = M; g.N = d; g.K = F; g.A = b.hid; g.lda = F; g.B = WL(l, L.w2); g.ldb = F;
     g.name = "gemm_ffn2";
     g.epi.bias = PL(l, L.b2); g.epi.drop = drop; g.epi.drop_site = site_ffn(l);
-    g.epi.res32 = b.x1_32; g.epi.ldres = d; g.epi.D32 = w.u32; g.epi.ldd32 = d;
-    AMC_TRY(gemm<E>(g, st));
-    AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
-                      sizeof(E) == 2 ? w.x32[xout] : nullptr, (E*)b.xhat2, b.rstd2, st));
+    g.epi.res32 = b.x1_32; g.epi.ldres = d;
+    if (fuse_ln()) {
+      g.name = "gemm_ffn2_ln";
+      g.epi.ln_gamma = PL(l, L.g2); g.epi.ln_beta = PL(l, L.be2); g.epi.ln_eps = D.ln_eps;
+      g.epi.D16 = w.x16[xout]; g.epi.ldd16 = d; g.epi.D32 = w.x32[xout]; g.epi.ldd32 = d;
+      g.epi.ln_xhat = b.xhat2; g.epi.ln_rstd = b.rstd2;
+      AMC_TRY(gemm<E>(g, st));
+    } else {
+      g.epi.D32 = w.u32; g.epi.ldd32 = d;
+      AMC_TRY(gemm<E>(g, st));
+      AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
+                        sizeof(E) == 2 ? w.x32[xout] : nullptr, (E*)b.xhat2, b.rstd2, st));
+    }
     return 0;
   }
 
@@ -565,6 +585,27 @@ int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA,
   if (dtype == AMC_BF16) return gemm_bf16(g, (cudaStream_t)stream);
   AMC_CHECK_ARG(dtype == AMC_F32, "unknown dtype %d", dtype);
   return gemm_f32(g, (cudaStream_t)stream);
+}
+
+int amc_gemm_ln(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                const float* res32, const float* gamma, const float* beta, float eps, void* y16, float* y32,
+                void* xhat, float* rstd, amc_stream_t stream) {
+  AMC_CHECK_ARG(A && B && res32 && gamma && beta && y16 && y32, "NULL argument");
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb;
+  g.epi.bias = bias; g.epi.res32 = res32; g.epi.ldres = N; g.epi.ln_gamma = gamma; g.epi.ln_beta = beta;
+  g.epi.ln_eps = eps; g.epi.D16 = y16; g.epi.ldd16 = N; g.epi.D32 = y32; g.epi.ldd32 = N; g.epi.ln_xhat = xhat;
+  g.epi.ln_rstd = rstd;
+  return gemm_bf16(g, (cudaStream_t)stream);
+}
+
+int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const void* mask,
+                       float mask_scale, void* D16, amc_stream_t stream) {
+  AMC_CHECK_ARG(A && B && mask && D16, "NULL argument");
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb;
+  g.epi.mask_src = mask; g.epi.ldmask = N; g.epi.mask_scale = mask_scale; g.epi.D16 = D16; g.epi.ldd16 = N;
+  return gemm_bf16(g, (cudaStream_t)stream);
 }
 
 int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream) {

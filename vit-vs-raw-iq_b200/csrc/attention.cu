@@ -213,31 +213,65 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(int T, int h, int dh, con
 
 
 // ---------------------------------------------------------------------------------------------
-// Small-sequence variant (T <= 32 tokens, head dim <= 32, e.g. ViT patch 16: T = 9): one THREAD per
-// (frame, head, query row); a CTA packs as many (frame, head) pairs as fit so all lanes work.
-// Q/K/V (and dO) of the CTA's pairs are staged in shared memory as fp32 with coalesced vector loads;
-// results go back through the same tiles so global stores are coalesced too.
+// Small-sequence variant (T <= 32 tokens, head dim <= 32 and % 4 == 0, e.g. ViT patch 16: T = 9):
+// one THREAD per (frame, head, query row); a CTA packs as many (frame, head) pairs as fit so all
+// lanes work.  Q/K/V (and dO) of the CTA's pairs are staged in shared memory as fp32 (row stride
+// DHP = 36 floats: 16-byte aligned rows, conflict-free float4 access); each thread keeps its own
+// q / dO / output rows in registers and streams K/V rows as broadcast float4 loads.  Results go
+// back through the same tiles so global stores are coalesced 16-byte vectors.
 // ---------------------------------------------------------------------------------------------
+constexpr int DHP = 36;   // padded head-dim stride (floats) of the staging tiles, dh <= 32
+
 template <typename E>
-__device__ __forceinline__ void small_load(float* dst, int stride, const E* __restrict__ src, int ld, int rows, int dh,
-                                           int tid, int nthreads) {
+__device__ __forceinline__ void small_load(float* dst, const E* __restrict__ src, int ld, int rows, int dh, int tid,
+                                           int nthreads) {
   const int q = dh >> 2;
   for (int i = tid; i < rows * q; i += nthreads) {
     const int r = i / q, c = (i - r * q) * 4;
-    const float4 v = load4(src + (size_t)r * ld + c);
-    float* o = dst + r * stride + c;
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    *reinterpret_cast<float4*>(dst + r * DHP + c) = load4(src + (size_t)r * ld + c);
   }
 }
 template <typename E>
-__device__ __forceinline__ void small_store(E* __restrict__ dst, int ld, const float* src, int stride, int rows, int dh,
-                                            int tid, int nthreads) {
+__device__ __forceinline__ void small_store(E* __restrict__ dst, int ld, const float* src, int rows, int dh, int tid,
+                                            int nthreads) {
   const int q = dh >> 2;
   for (int i = tid; i < rows * q; i += nthreads) {
     const int r = i / q, c = (i - r * q) * 4;
-    const float* o = src + r * stride + c;
-    store4(dst + (size_t)r * ld + c, make_float4(o[0], o[1], o[2], o[3]));
+    store4(dst + (size_t)r * ld + c, *reinterpret_cast<const float4*>(src + r * DHP + c));
   }
+}
+// row (8 float4) <-> registers; only the first dh/4 vectors are live
+__device__ __forceinline__ void row_load(float4 (&r)[8], const float* p, int nq) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = k < nq ? *reinterpret_cast<const float4*>(p + 4 * k) : make_float4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void row_store(float* p, const float4 (&r)[8], int nq) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < nq) *reinterpret_cast<float4*>(p + 4 * k) = r[k];
+}
+__device__ __forceinline__ float row_dot(const float4 (&a)[8], const float* p, int nq) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < nq) {
+      const float4 b = *reinterpret_cast<const float4*>(p + 4 * k);
+      s = fmaf(a[k].x, b.x, s); s = fmaf(a[k].y, b.y, s); s = fmaf(a[k].z, b.z, s); s = fmaf(a[k].w, b.w, s);
+    }
+  return s;
+}
+__device__ __forceinline__ void row_axpy(float4 (&acc)[8], float w, const float* p, int nq) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < nq) {
+      const float4 b = *reinterpret_cast<const float4*>(p + 4 * k);
+      acc[k].x = fmaf(w, b.x, acc[k].x); acc[k].y = fmaf(w, b.y, acc[k].y);
+      acc[k].z = fmaf(w, b.z, acc[k].z); acc[k].w = fmaf(w, b.w, acc[k].w);
+    }
+}
+__device__ __forceinline__ void row_zero(float4 (&r)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = make_float4(0, 0, 0, 0);
 }
 
 template <typename E, int MAXT>
@@ -246,16 +280,16 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(int npairs, int T, 
                                                              float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sm = reinterpret_cast<float*>(smem_raw);
-  const int d = h * dh, ld = 3 * d, stride = dh + 1, tile = T * stride;
+  const int d = h * dh, ld = 3 * d, tile = T * DHP, nq = dh >> 2;
   const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int p = 0; p < np; ++p) {
     const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
     const E* base = qkv + (size_t)b * T * ld + hh * dh;
     float* Q = sm + p * 3 * tile;
-    small_load(Q, stride, base, ld, T, dh, tid, nt);
-    small_load(Q + tile, stride, base + d, ld, T, dh, tid, nt);
-    small_load(Q + 2 * tile, stride, base + 2 * d, ld, T, dh, tid, nt);
+    small_load(Q, base, ld, T, dh, tid, nt);
+    small_load(Q + tile, base + d, ld, T, dh, tid, nt);
+    small_load(Q + 2 * tile, base + 2 * d, ld, T, dh, tid, nt);
   }
   __syncthreads();
   const int p = tid / T, i = tid - p * T;
@@ -263,19 +297,14 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(int npairs, int T, 
     float* Q = sm + p * 3 * tile;
     const float* K = Q + tile;
     const float* V = Q + 2 * tile;
-    float* q = Q + i * stride;
+    float4 q[8];
+    row_load(q, Q + i * DHP, nq);
     float s[MAXT];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
-      float a = -INFINITY;
-      if (j < T) {
-        a = 0.f;
-        for (int c = 0; c < dh; ++c) a = fmaf(q[c], K[j * stride + c], a);
-        a *= scale;
-      }
-      s[j] = a;
-      mx = fmaxf(mx, a);
+      s[j] = j < T ? row_dot(q, K + j * DHP, nq) * scale : -INFINITY;
+      mx = fmaxf(mx, s[j]);
     }
     float l = 0.f;
 #pragma unroll
@@ -284,18 +313,17 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(int npairs, int T, 
       l += s[j];
     }
     const float inv = 1.f / l;
-    for (int c = 0; c < dh; ++c) {
-      float a = 0.f;
+    float4 o[8];
+    row_zero(o);
 #pragma unroll
-      for (int j = 0; j < MAXT; ++j)
-        if (j < T) a = fmaf(s[j], V[j * stride + c], a);
-      q[c] = a * inv;                       // own q row is dead: reuse it as the output staging row
-    }
+    for (int j = 0; j < MAXT; ++j)
+      if (j < T) row_axpy(o, s[j] * inv, V + j * DHP, nq);
+    row_store(Q + i * DHP, o, nq);          // own q row is dead: reuse it as the output staging row
   }
   __syncthreads();
   for (int pp = 0; pp < np; ++pp) {
     const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
-    small_store(out + (size_t)b * T * d + hh * dh, d, sm + pp * 3 * tile, stride, T, dh, tid, nt);
+    small_store(out + (size_t)b * T * d + hh * dh, d, sm + pp * 3 * tile, T, dh, tid, nt);
   }
 }
 
@@ -305,18 +333,18 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(int npairs, int T, 
                                                              E* __restrict__ dqkv, float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sm = reinterpret_cast<float*>(smem_raw);
-  const int d = h * dh, ld = 3 * d, stride = dh + 1, tile = T * stride, pt = T * (T + 1);
-  const int per_pair = 4 * tile + 2 * pt;
+  const int d = h * dh, ld = 3 * d, tile = T * DHP, pt = T * (T + 1), nq = dh >> 2;
+  const int per_pair = 4 * tile + 2 * pt + ((2 * pt) & 3 ? 4 - ((2 * pt) & 3) : 0);   // keep tiles 16B aligned
   const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int p = 0; p < np; ++p) {
     const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
     const E* base = qkv + (size_t)b * T * ld + hh * dh;
     float* Q = sm + p * per_pair;
-    small_load(Q, stride, base, ld, T, dh, tid, nt);
-    small_load(Q + tile, stride, base + d, ld, T, dh, tid, nt);
-    small_load(Q + 2 * tile, stride, base + 2 * d, ld, T, dh, tid, nt);
-    small_load(Q + 3 * tile, stride, dout + (size_t)b * T * d + hh * dh, d, T, dh, tid, nt);
+    small_load(Q, base, ld, T, dh, tid, nt);
+    small_load(Q + tile, base + d, ld, T, dh, tid, nt);
+    small_load(Q + 2 * tile, base + 2 * d, ld, T, dh, tid, nt);
+    small_load(Q + 3 * tile, dout + (size_t)b * T * d + hh * dh, d, T, dh, tid, nt);
   }
   __syncthreads();
   const int p = tid / T, i = tid - p * T;
@@ -328,24 +356,16 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(int npairs, int T, 
   float* P = Q + 4 * tile;
   float* dS = P + pt;
   if (act) {   // phase 1: row i of P and dS
-    const float* q = Q + i * stride;
-    const float* o = dO + i * stride;
+    float4 q[8], o[8];
+    row_load(q, Q + i * DHP, nq);
+    row_load(o, dO + i * DHP, nq);
     float s[MAXT], dp[MAXT];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
-      float a = -INFINITY, g = 0.f;
-      if (j < T) {
-        a = 0.f;
-        for (int c = 0; c < dh; ++c) {
-          a = fmaf(q[c], K[j * stride + c], a);
-          g = fmaf(o[c], V[j * stride + c], g);
-        }
-        a *= scale;
-      }
-      s[j] = a;
-      dp[j] = g;
-      mx = fmaxf(mx, a);
+      s[j] = j < T ? row_dot(q, K + j * DHP, nq) * scale : -INFINITY;
+      dp[j] = j < T ? row_dot(o, V + j * DHP, nq) : 0.f;
+      mx = fmaxf(mx, s[j]);
     }
     float l = 0.f;
 #pragma unroll
@@ -368,41 +388,29 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(int npairs, int T, 
       }
   }
   __syncthreads();
-  float dq[32], dk[32], dv[32];
+  float4 dq[8], dk[8], dv[8];
+  row_zero(dq); row_zero(dk); row_zero(dv);
   if (act) {   // phase 2: dQ_i (as query row i) and dK_i, dV_i (as key row i)
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { dq[c] = 0.f; dk[c] = 0.f; dv[c] = 0.f; }
     for (int j = 0; j < T; ++j) {
-      const float ds_ij = dS[i * (T + 1) + j];     // query i, key j
-      const float ds_ji = dS[j * (T + 1) + i];     // query j, key i
-      const float p_ji = P[j * (T + 1) + i];
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < dh) {
-          dq[c] = fmaf(ds_ij, K[j * stride + c], dq[c]);
-          dk[c] = fmaf(ds_ji, Q[j * stride + c], dk[c]);
-          dv[c] = fmaf(p_ji, dO[j * stride + c], dv[c]);
-        }
+      row_axpy(dq, dS[i * (T + 1) + j], K + j * DHP, nq);    // query i, key j
+      row_axpy(dk, dS[j * (T + 1) + i], Q + j * DHP, nq);    // query j, key i
+      row_axpy(dv, P[j * (T + 1) + i], dO + j * DHP, nq);
     }
   }
   __syncthreads();   // every read of Q/K/V/dO is done: reuse the tiles as output staging
   if (act) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < dh) {
-        Q[i * stride + c] = dq[c];
-        K[i * stride + c] = dk[c];
-        V[i * stride + c] = dv[c];
-      }
+    row_store(Q + i * DHP, dq, nq);
+    row_store(K + i * DHP, dk, nq);
+    row_store(V + i * DHP, dv, nq);
   }
   __syncthreads();
   for (int pp = 0; pp < np; ++pp) {
     const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
     E* base = dqkv + (size_t)b * T * ld + hh * dh;
     const float* S = sm + pp * per_pair;
-    small_store(base, ld, S, stride, T, dh, tid, nt);
-    small_store(base + d, ld, S + tile, stride, T, dh, tid, nt);
-    small_store(base + 2 * d, ld, S + 2 * tile, stride, T, dh, tid, nt);
+    small_store(base, ld, S, T, dh, tid, nt);
+    small_store(base + d, ld, S + tile, T, dh, tid, nt);
+    small_store(base + 2 * d, ld, S + 2 * tile, T, dh, tid, nt);
   }
 }
 
@@ -424,7 +432,7 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
   if (use_small(T, dh)) {
-    const size_t per_pair = (size_t)3 * T * (dh + 1) * sizeof(float);
+    const size_t per_pair = (size_t)3 * T * DHP * sizeof(float);
     const int ppc = small_ppc(T, per_pair), npairs = B * h;
     const size_t sm = per_pair * ppc;
     const int threads = ((ppc * T + 31) / 32) * 32;
@@ -459,7 +467,7 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
   if (use_small(T, dh)) {
-    const size_t per_pair = ((size_t)4 * T * (dh + 1) + 2 * T * (T + 1)) * sizeof(float);
+    const size_t per_pair = (((size_t)4 * T * DHP + 2 * T * (T + 1) + 3) & ~(size_t)3) * sizeof(float);
     const int ppc = small_ppc(T, per_pair), npairs = B * h;
     const size_t sm = per_pair * ppc;
     const int threads = ((ppc * T + 31) / 32) * 32;

@@ -24,6 +24,13 @@ struct Epi {
   float* D32 = nullptr;
   int ldd32 = 0;
   int accumulate = 0;             // D32 += (atomic)
+  // fused LayerNorm over the row (bf16 tcgen05 path, N <= 256): u = epilogue value, y = gamma*xhat+beta ->
+  // D16 (bf16 y), D32 (fp32 y), ln_xhat (bf16, optional, pitch N), ln_rstd (fp32 [M], optional)
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 0.f;
+  void* ln_xhat = nullptr;
+  float* ln_rstd = nullptr;
 };
 
 // ---- fast path: whole float4 in bounds, every pointer vector-aligned; registers only -------------
