@@ -27,7 +27,7 @@ __device__ __forceinline__ void load_head_tile(E* dst, int stride, const E* __re
 template <typename E>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(int T, int h, int dh, const E* __restrict__ qkv,
                                                        E* __restrict__ out, float scale) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = h * dh, ld = 3 * d;
   const int stride = dh + SmemPad<E>::v;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +90,7 @@ template <typename E>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(int T, int h, int dh, const E* __restrict__ qkv,
                                                        const E* __restrict__ dout, E* __restrict__ dqkv,
                                                        float scale) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = h * dh, ld = 3 * d;
   const int stride = dh + SmemPad<E>::v;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,58 +213,113 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(int T, int h, int dh, con
 
 
 // ---------------------------------------------------------------------------------------------
-// Small-sequence variant (T <= 32 tokens, head dim <= 32 and % 4 == 0, e.g. ViT patch 16: T = 9):
-// one THREAD per (frame, head, query row); a CTA packs as many (frame, head) pairs as fit so all
-// lanes work.  Q/K/V (and dO) of the CTA's pairs are staged in shared memory as fp32 (row stride
-// DHP = 36 floats: 16-byte aligned rows, conflict-free float4 access); each thread keeps its own
-// q / dO / output rows in registers and streams K/V rows as broadcast float4 loads.  Results go
-// back through the same tiles so global stores are coalesced 16-byte vectors.
+// Small-sequence variant (T <= 32 tokens, head dim <= 32 and % 4 == 0, e.g. ViT patch 16: T = 9).
+// A CTA owns whole FRAMES: the [T, 3d] q|k|v rows of a frame are contiguous in HBM, so staging is a
+// straight 16-byte-vector copy (no gather), kept in the storage dtype; rows get 16 B of padding so the
+// per-thread row reads spread over the banks.  One THREAD per (frame, head, query row) keeps its q / dO /
+// output rows in registers and streams K/V rows as broadcast vector loads.  Results are staged in shared
+// memory and leave as 16-byte row copies.  The grid is persistent (a few CTAs per SM loop over frames).
 // ---------------------------------------------------------------------------------------------
-constexpr int DHP = 36;   // padded head-dim stride (floats) of the staging tiles, dh <= 32
+template <typename E> struct Vec16 { static constexpr int n = 16 / sizeof(E); };   // elements per 16 bytes
 
-template <typename E>
-__device__ __forceinline__ void small_load(float* dst, const E* __restrict__ src, int ld, int rows, int dh, int tid,
-                                           int nthreads) {
-  const int q = dh >> 2;
-  for (int i = tid; i < rows * q; i += nthreads) {
-    const int r = i / q, c = (i - r * q) * 4;
-    *reinterpret_cast<float4*>(dst + r * DHP + c) = load4(src + (size_t)r * ld + c);
+// copy `rows` rows of `row_elems` elements between a dense global block and a padded smem block
+template <typename E, bool TO_SMEM>
+__device__ __forceinline__ void rows_copy(E* smem_blk, int smem_stride, E* gmem_blk, int rows, int row_elems, int tid,
+                                          int nt) {
+  const int vpr = row_elems / Vec16<E>::n;      // vectors per row
+  int r = tid / vpr, c = tid - r * vpr;
+  const int dr = nt / vpr, dc = nt - dr * vpr;
+  while (r < rows) {
+    uint4* sp = reinterpret_cast<uint4*>(smem_blk + (size_t)r * smem_stride) + c;
+    uint4* gp = reinterpret_cast<uint4*>(gmem_blk + (size_t)r * row_elems) + c;
+    if (TO_SMEM) *sp = *gp;
+    else *gp = *sp;
+    r += dr;
+    c += dc;
+    if (c >= vpr) { c -= vpr; ++r; }
   }
 }
-template <typename E>
-__device__ __forceinline__ void small_store(E* __restrict__ dst, int ld, const float* src, int rows, int dh, int tid,
-                                            int nthreads) {
-  const int q = dh >> 2;
-  for (int i = tid; i < rows * q; i += nthreads) {
-    const int r = i / q, c = (i - r * q) * 4;
-    store4(dst + (size_t)r * ld + c, *reinterpret_cast<const float4*>(src + r * DHP + c));
+
+// ---- 1-D bulk (TMA) row copies: one elected thread moves whole rows, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
   }
 }
-// row (8 float4) <-> registers; only the first dh/4 vectors are live
-__device__ __forceinline__ void row_load(float4 (&r)[8], const float* p, int nq) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// load `rows` dense global rows into padded smem rows (called by ONE thread)
+template <typename E>
+__device__ __forceinline__ void bulk_rows_in(E* smem_blk, int smem_stride, const E* gmem_blk, int rows, int row_elems,
+                                             uint64_t* bar) {
+  const uint32_t rb = (uint32_t)(row_elems * sizeof(E));
+  mbar_expect(bar, rb * (uint32_t)rows);
+  for (int r = 0; r < rows; ++r) bulk_g2s(smem_blk + (size_t)r * smem_stride, gmem_blk + (size_t)r * row_elems, rb, bar);
+}
+template <typename E>
+__device__ __forceinline__ void bulk_rows_out(E* gmem_blk, const E* smem_blk, int smem_stride, int rows, int row_elems) {
+  const uint32_t rb = (uint32_t)(row_elems * sizeof(E));
+  for (int r = 0; r < rows; ++r) bulk_s2g(gmem_blk + (size_t)r * row_elems, smem_blk + (size_t)r * smem_stride, rb);
+  bulk_commit_group();
+}
+
+// row (<= 32 elements) <-> registers; only the first nq float4 are live
+template <typename E>
+__device__ __forceinline__ void row_load(float4 (&r)[8], const E* p, int nq) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = k < nq ? *reinterpret_cast<const float4*>(p + 4 * k) : make_float4(0, 0, 0, 0);
+  for (int k = 0; k < 8; ++k) r[k] = k < nq ? load4(p + 4 * k) : make_float4(0, 0, 0, 0);
 }
-__device__ __forceinline__ void row_store(float* p, const float4 (&r)[8], int nq) {
+template <typename E>
+__device__ __forceinline__ void row_store(E* p, const float4 (&r)[8], int nq) {
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    if (k < nq) *reinterpret_cast<float4*>(p + 4 * k) = r[k];
+    if (k < nq) store4(p + 4 * k, r[k]);
 }
-__device__ __forceinline__ float row_dot(const float4 (&a)[8], const float* p, int nq) {
+template <typename E>
+__device__ __forceinline__ float row_dot(const float4 (&a)[8], const E* p, int nq) {
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k)
     if (k < nq) {
-      const float4 b = *reinterpret_cast<const float4*>(p + 4 * k);
+      const float4 b = load4(p + 4 * k);
       s = fmaf(a[k].x, b.x, s); s = fmaf(a[k].y, b.y, s); s = fmaf(a[k].z, b.z, s); s = fmaf(a[k].w, b.w, s);
     }
   return s;
 }
-__device__ __forceinline__ void row_axpy(float4 (&acc)[8], float w, const float* p, int nq) {
+template <typename E>
+__device__ __forceinline__ void row_axpy(float4 (&acc)[8], float w, const E* p, int nq) {
 #pragma unroll
   for (int k = 0; k < 8; ++k)
     if (k < nq) {
-      const float4 b = *reinterpret_cast<const float4*>(p + 4 * k);
+      const float4 b = load4(p + 4 * k);
       acc[k].x = fmaf(w, b.x, acc[k].x); acc[k].y = fmaf(w, b.y, acc[k].y);
       acc[k].z = fmaf(w, b.z, acc[k].z); acc[k].w = fmaf(w, b.w, acc[k].w);
     }
@@ -275,151 +330,195 @@ __device__ __forceinline__ void row_zero(float4 (&r)[8]) {
 }
 
 template <typename E, int MAXT>
-__global__ void __launch_bounds__(256) attn_small_fwd_kernel(int npairs, int T, int h, int dh, int ppc,
-                                                             const E* __restrict__ qkv, E* __restrict__ out,
-                                                             float scale) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sm = reinterpret_cast<float*>(smem_raw);
-  const int d = h * dh, ld = 3 * d, tile = T * DHP, nq = dh >> 2;
-  const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int p = 0; p < np; ++p) {
-    const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
-    const E* base = qkv + (size_t)b * T * ld + hh * dh;
-    float* Q = sm + p * 3 * tile;
-    small_load(Q, base, ld, T, dh, tid, nt);
-    small_load(Q + tile, base + d, ld, T, dh, tid, nt);
-    small_load(Q + 2 * tile, base + 2 * d, ld, T, dh, tid, nt);
+__global__ void __launch_bounds__(256) attn_frames_fwd_kernel(int B, int T, int h, int dh, int F,
+                                                              const E* __restrict__ qkv, E* __restrict__ out,
+                                                              float scale) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = h * dh, ld = 3 * d, nq = dh >> 2;
+  const int s_in = ld + Vec16<E>::n, s_out = d + Vec16<E>::n;     // padded row strides (elements)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // [2] input buffers
+  E* blk0 = reinterpret_cast<E*>(smem_raw + 128);
+  const size_t in_elems = (size_t)F * T * s_in;
+  E* oblk = blk0 + 2 * in_elems;
+  const int tid = threadIdx.x;
+  const int hT = h * T;
+  const int f = tid / hT, rem = tid - f * hT, hh = rem / T, i = rem - hh * T;
+  if (tid == 0) {
+    mbar_init1(bars);
+    mbar_init1(bars + 1);
   }
   __syncthreads();
-  const int p = tid / T, i = tid - p * T;
-  if (p < np) {
-    float* Q = sm + p * 3 * tile;
-    const float* K = Q + tile;
-    const float* V = Q + 2 * tile;
-    float4 q[8];
-    row_load(q, Q + i * DHP, nq);
-    float s[MAXT];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
-      s[j] = j < T ? row_dot(q, K + j * DHP, nq) * scale : -INFINITY;
-      mx = fmaxf(mx, s[j]);
+  const int stride_f = gridDim.x * F;
+  int f0 = blockIdx.x * F;
+  if (tid == 0 && f0 < B) bulk_rows_in(blk0, s_in, qkv + (size_t)f0 * T * ld, min(F, B - f0) * T, ld, bars);
+  for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
+    const int nf = min(F, B - f0);
+    E* blk = blk0 + (it & 1) * in_elems;
+    if (tid == 0) {
+      const int fn = f0 + stride_f;           // prefetch the next frames into the other buffer
+      if (fn < B) bulk_rows_in(blk0 + ((it + 1) & 1) * in_elems, s_in, qkv + (size_t)fn * T * ld, min(F, B - fn) * T, ld,
+                               bars + ((it + 1) & 1));
     }
-    float l = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
-      s[j] = j < T ? __expf(s[j] - mx) : 0.f;
-      l += s[j];
-    }
-    const float inv = 1.f / l;
+    mbar_wait_parity(bars + (it & 1), (it >> 1) & 1);
     float4 o[8];
-    row_zero(o);
+    if (f < nf) {
+      const E* fb = blk + (size_t)f * T * s_in + hh * dh;
+      float4 q[8];
+      row_load(q, fb + (size_t)i * s_in, nq);
+      float s[MAXT];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXT; ++j)
-      if (j < T) row_axpy(o, s[j] * inv, V + j * DHP, nq);
-    row_store(Q + i * DHP, o, nq);          // own q row is dead: reuse it as the output staging row
+      for (int j = 0; j < MAXT; ++j) {
+        s[j] = j < T ? row_dot(q, fb + (size_t)j * s_in + d, nq) * scale : -INFINITY;
+        mx = fmaxf(mx, s[j]);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) {
+        s[j] = j < T ? __expf(s[j] - mx) : 0.f;
+        l += s[j];
+      }
+      const float inv = 1.f / l;
+      row_zero(o);
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j)
+        if (j < T) row_axpy(o, s[j] * inv, fb + (size_t)j * s_in + 2 * d, nq);
+    }
+    if (tid == 0) bulk_wait_read0();          // previous iteration's output rows have left oblk
+    __syncthreads();                          // ... and everyone is done reading blk (it may be refilled next iteration)
+    if (f < nf) row_store(oblk + ((size_t)f * T + i) * s_out + hh * dh, o, nq);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) bulk_rows_out(out + (size_t)f0 * T * d, oblk, s_out, nf * T, d);
   }
-  __syncthreads();
-  for (int pp = 0; pp < np; ++pp) {
-    const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
-    small_store(out + (size_t)b * T * d + hh * dh, d, sm + pp * 3 * tile, T, dh, tid, nt);
-  }
+  if (tid == 0) bulk_wait_all0();
 }
 
 template <typename E, int MAXT>
-__global__ void __launch_bounds__(256) attn_small_bwd_kernel(int npairs, int T, int h, int dh, int ppc,
-                                                             const E* __restrict__ qkv, const E* __restrict__ dout,
-                                                             E* __restrict__ dqkv, float scale) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sm = reinterpret_cast<float*>(smem_raw);
-  const int d = h * dh, ld = 3 * d, tile = T * DHP, pt = T * (T + 1), nq = dh >> 2;
-  const int per_pair = 4 * tile + 2 * pt + ((2 * pt) & 3 ? 4 - ((2 * pt) & 3) : 0);   // keep tiles 16B aligned
-  const int pair0 = blockIdx.x * ppc, np = min(ppc, npairs - pair0);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int p = 0; p < np; ++p) {
-    const int pair = pair0 + p, b = pair / h, hh = pair - b * h;
-    const E* base = qkv + (size_t)b * T * ld + hh * dh;
-    float* Q = sm + p * per_pair;
-    small_load(Q, base, ld, T, dh, tid, nt);
-    small_load(Q + tile, base + d, ld, T, dh, tid, nt);
-    small_load(Q + 2 * tile, base + 2 * d, ld, T, dh, tid, nt);
-    small_load(Q + 3 * tile, dout + (size_t)b * T * d + hh * dh, d, T, dh, tid, nt);
-  }
+__global__ void __launch_bounds__(256) attn_frames_bwd_kernel(int B, int T, int h, int dh, int F,
+                                                              const E* __restrict__ qkv, const E* __restrict__ dout,
+                                                              E* __restrict__ dqkv, float scale) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = h * dh, ld = 3 * d, nq = dh >> 2, pt = T * (T + 1);
+  const int s_in = ld + Vec16<E>::n, s_do = d + Vec16<E>::n;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  E* blk = reinterpret_cast<E*>(smem_raw + 128);
+  E* doblk = blk + (size_t)F * T * s_in;
+  E* oblk = doblk + (size_t)F * T * s_do;                          // dq|dk|dv staging
+  float* pbase = reinterpret_cast<float*>(oblk + (size_t)F * T * s_in);   // [F*h][2][T][T+1]
+  const int tid = threadIdx.x;
+  const int hT = h * T;
+  const int f = tid / hT, rem = tid - f * hT, hh = rem / T, i = rem - hh * T;
+  if (tid == 0) mbar_init1(bar);
   __syncthreads();
-  const int p = tid / T, i = tid - p * T;
-  const bool act = p < np;
-  float* Q = sm + (act ? p : 0) * per_pair;
-  float* K = Q + tile;
-  float* V = Q + 2 * tile;
-  float* dO = Q + 3 * tile;
-  float* P = Q + 4 * tile;
-  float* dS = P + pt;
-  if (act) {   // phase 1: row i of P and dS
-    float4 q[8], o[8];
-    row_load(q, Q + i * DHP, nq);
-    row_load(o, dO + i * DHP, nq);
-    float s[MAXT], dp[MAXT];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
-      s[j] = j < T ? row_dot(q, K + j * DHP, nq) * scale : -INFINITY;
-      dp[j] = j < T ? row_dot(o, V + j * DHP, nq) : 0.f;
-      mx = fmaxf(mx, s[j]);
+  const int stride_f = gridDim.x * F;
+  int f0 = blockIdx.x * F;
+  if (tid == 0 && f0 < B) {
+    const int rows = min(F, B - f0) * T;
+    mbar_expect(bar, (uint32_t)(rows * (ld + d) * sizeof(E)));
+    for (int r = 0; r < rows; ++r) {
+      bulk_g2s(blk + (size_t)r * s_in, qkv + ((size_t)f0 * T + r) * ld, (uint32_t)(ld * sizeof(E)), bar);
+      bulk_g2s(doblk + (size_t)r * s_do, dout + ((size_t)f0 * T + r) * d, (uint32_t)(d * sizeof(E)), bar);
     }
-    float l = 0.f;
+  }
+  for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
+    const int nf = min(F, B - f0);
+    mbar_wait_parity(bar, it & 1);
+    const bool act = f < nf;
+    const E* fb = blk + (size_t)(act ? f : 0) * T * s_in + hh * dh;          // q at +0, k at +d, v at +2d
+    const E* fo = doblk + (size_t)(act ? f : 0) * T * s_do + hh * dh;
+    float* P = pbase + (size_t)((act ? f : 0) * h + hh) * 2 * pt;
+    float* dS = P + pt;
+    if (act) {   // phase 1: row i of P and dS
+      float4 q[8], o[8];
+      row_load(q, fb + (size_t)i * s_in, nq);
+      row_load(o, fo + (size_t)i * s_do, nq);
+      float s[MAXT], dp[MAXT];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
-      s[j] = j < T ? __expf(s[j] - mx) : 0.f;
-      l += s[j];
-    }
-    const float inv = 1.f / l;
-    float dl = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
-      s[j] *= inv;
-      dl = fmaf(s[j], dp[j], dl);
-    }
-#pragma unroll
-    for (int j = 0; j < MAXT; ++j)
-      if (j < T) {
-        P[i * (T + 1) + j] = s[j];
-        dS[i * (T + 1) + j] = s[j] * (dp[j] - dl) * scale;
+      for (int j = 0; j < MAXT; ++j) {
+        s[j] = j < T ? row_dot(q, fb + (size_t)j * s_in + d, nq) * scale : -INFINITY;
+        dp[j] = j < T ? row_dot(o, fb + (size_t)j * s_in + 2 * d, nq) : 0.f;
+        mx = fmaxf(mx, s[j]);
       }
-  }
-  __syncthreads();
-  float4 dq[8], dk[8], dv[8];
-  row_zero(dq); row_zero(dk); row_zero(dv);
-  if (act) {   // phase 2: dQ_i (as query row i) and dK_i, dV_i (as key row i)
-    for (int j = 0; j < T; ++j) {
-      row_axpy(dq, dS[i * (T + 1) + j], K + j * DHP, nq);    // query i, key j
-      row_axpy(dk, dS[j * (T + 1) + i], Q + j * DHP, nq);    // query j, key i
-      row_axpy(dv, P[j * (T + 1) + i], dO + j * DHP, nq);
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) {
+        s[j] = j < T ? __expf(s[j] - mx) : 0.f;
+        l += s[j];
+      }
+      const float inv = 1.f / l;
+      float dl = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) {
+        s[j] *= inv;
+        dl = fmaf(s[j], dp[j], dl);
+      }
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j)
+        if (j < T) {
+          P[i * (T + 1) + j] = s[j];
+          dS[i * (T + 1) + j] = s[j] * (dp[j] - dl) * scale;
+        }
     }
+    __syncthreads();
+    float4 dq[8], dk[8], dv[8];
+    row_zero(dq); row_zero(dk); row_zero(dv);
+    if (act) {   // phase 2: dQ_i (as query row i) and dK_i, dV_i (as key row i)
+      for (int j = 0; j < T; ++j) {
+        row_axpy(dq, dS[i * (T + 1) + j], fb + (size_t)j * s_in + d, nq);    // query i, key j
+        row_axpy(dk, dS[j * (T + 1) + i], fb + (size_t)j * s_in, nq);        // query j, key i
+        row_axpy(dv, P[j * (T + 1) + i], fo + (size_t)j * s_do, nq);
+      }
+    }
+    if (tid == 0) bulk_wait_read0();          // previous iteration's gradient rows have left oblk
+    __syncthreads();                          // every read of q/k/v/dO is done: inputs may be refilled
+    if (tid == 0) {
+      const int fn = f0 + stride_f;
+      if (fn < B) {
+        const int rows = min(F, B - fn) * T;
+        mbar_expect(bar, (uint32_t)(rows * (ld + d) * sizeof(E)));
+        for (int r = 0; r < rows; ++r) {
+          bulk_g2s(blk + (size_t)r * s_in, qkv + ((size_t)fn * T + r) * ld, (uint32_t)(ld * sizeof(E)), bar);
+          bulk_g2s(doblk + (size_t)r * s_do, dout + ((size_t)fn * T + r) * d, (uint32_t)(d * sizeof(E)), bar);
+        }
+      }
+    }
+    if (act) {
+      E* ob = oblk + ((size_t)f * T + i) * s_in + hh * dh;
+      row_store(ob, dq, nq);
+      row_store(ob + d, dk, nq);
+      row_store(ob + 2 * d, dv, nq);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) bulk_rows_out(dqkv + (size_t)f0 * T * ld, oblk, s_in, nf * T, ld);
   }
-  __syncthreads();   // every read of Q/K/V/dO is done: reuse the tiles as output staging
-  if (act) {
-    row_store(Q + i * DHP, dq, nq);
-    row_store(K + i * DHP, dk, nq);
-    row_store(V + i * DHP, dv, nq);
-  }
-  __syncthreads();
-  for (int pp = 0; pp < np; ++pp) {
-    const int pair = pair0 + pp, b = pair / h, hh = pair - b * h;
-    E* base = dqkv + (size_t)b * T * ld + hh * dh;
-    const float* S = sm + pp * per_pair;
-    small_store(base, ld, S, T, dh, tid, nt);
-    small_store(base + d, ld, S + tile, T, dh, tid, nt);
-    small_store(base + 2 * d, ld, S + 2 * tile, T, dh, tid, nt);
-  }
+  if (tid == 0) bulk_wait_all0();
 }
 
-inline bool use_small(int T, int dh) { return T <= 32 && dh <= 32 && dh % 4 == 0; }
-// pairs per CTA: fill <= 256 threads and <= ~72 KB of shared memory (3 CTAs per SM)
-inline int small_ppc(int T, size_t bytes_per_pair) {
-  int ppc = std::max(1, 256 / T);
-  ppc = std::min<int>(ppc, std::max<size_t>(1, (72 * 1024) / bytes_per_pair));
-  return ppc;
+// the frame kernels need 16-byte row copies: (3d, d) * sizeof(E) % 16 == 0
+template <typename E>
+inline bool use_small(int T, int h, int dh) {
+  return T <= 32 && dh <= 32 && dh % 4 == 0 && (h * dh) % Vec16<E>::n == 0 && h * T <= 256;
+}
+template <typename E>
+inline size_t small_fwd_bytes(int T, int h, int dh, int F) {
+  const int d = h * dh;
+  return 128 + ((size_t)2 * F * T * (3 * d + Vec16<E>::n) + (size_t)F * T * (d + Vec16<E>::n)) * sizeof(E);
+}
+template <typename E>
+inline size_t small_bwd_bytes(int T, int h, int dh, int F) {
+  const int d = h * dh;
+  return 128 + ((size_t)2 * F * T * (3 * d + Vec16<E>::n) + (size_t)F * T * (d + Vec16<E>::n)) * sizeof(E) +
+         (size_t)F * h * 2 * T * (T + 1) * sizeof(float);
+}
+// frames per CTA iteration: <= 256 threads and <= ~72 KB of shared memory (3 CTAs per SM)
+template <typename E, typename BytesFn>
+inline int small_frames(int T, int h, int dh, BytesFn bytes) {
+  int F = std::max(1, 256 / (h * T));
+  while (F > 1 && bytes(T, h, dh, F) > 100 * 1024) --F;
+  return F;
 }
 
 inline int pick_warps(int T) { return std::max(1, std::min(8, (T + 7) / 8)); }
@@ -431,19 +530,19 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
-  if (use_small(T, dh)) {
-    const size_t per_pair = (size_t)3 * T * DHP * sizeof(float);
-    const int ppc = small_ppc(T, per_pair), npairs = B * h;
-    const size_t sm = per_pair * ppc;
-    const int threads = ((ppc * T + 31) / 32) * 32;
+  if (use_small<E>(T, h, dh)) {
+    const int F = small_frames<E>(T, h, dh, small_fwd_bytes<E>);
+    const size_t sm = small_fwd_bytes<E>(T, h, dh, F);
+    AMC_CHECK_ARG(sm <= 200 * 1024, "attention: frame tile needs %zu bytes of shared memory", sm);
+    const int threads = ((F * h * T + 31) / 32) * 32;
+    const int grid = std::min(ceil_div(B, F), 148 * 2);
+    const float sc = 1.f / sqrtf((float)dh);
     if (T <= 16) {
-      if (sm > 48 * 1024)
-        AMC_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attn_small_fwd_kernel<E, 16><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, out, 1.f / sqrtf((float)dh));
+      AMC_CUDA(cudaFuncSetAttribute(attn_frames_fwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attn_frames_fwd_kernel<E, 16><<<grid, threads, sm, st>>>(B, T, h, dh, F, qkv, out, sc);
     } else {
-      if (sm > 48 * 1024)
-        AMC_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attn_small_fwd_kernel<E, 32><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, out, 1.f / sqrtf((float)dh));
+      AMC_CUDA(cudaFuncSetAttribute(attn_frames_fwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attn_frames_fwd_kernel<E, 32><<<grid, threads, sm, st>>>(B, T, h, dh, F, qkv, out, sc);
     }
     AMC_LAUNCH_CHECK();
     return 0;
@@ -466,19 +565,19 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
-  if (use_small(T, dh)) {
-    const size_t per_pair = (((size_t)4 * T * DHP + 2 * T * (T + 1) + 3) & ~(size_t)3) * sizeof(float);
-    const int ppc = small_ppc(T, per_pair), npairs = B * h;
-    const size_t sm = per_pair * ppc;
-    const int threads = ((ppc * T + 31) / 32) * 32;
+  if (use_small<E>(T, h, dh)) {
+    const int F = small_frames<E>(T, h, dh, small_bwd_bytes<E>);
+    const size_t sm = small_bwd_bytes<E>(T, h, dh, F);
+    AMC_CHECK_ARG(sm <= 200 * 1024, "attention_bwd: frame tile needs %zu bytes of shared memory", sm);
+    const int threads = ((F * h * T + 31) / 32) * 32;
+    const int grid = std::min(ceil_div(B, F), 148 * 2);
+    const float sc = 1.f / sqrtf((float)dh);
     if (T <= 16) {
-      if (sm > 48 * 1024)
-        AMC_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attn_small_bwd_kernel<E, 16><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, dout, dqkv, 1.f / sqrtf((float)dh));
+      AMC_CUDA(cudaFuncSetAttribute(attn_frames_bwd_kernel<E, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attn_frames_bwd_kernel<E, 16><<<grid, threads, sm, st>>>(B, T, h, dh, F, qkv, dout, dqkv, sc);
     } else {
-      if (sm > 48 * 1024)
-        AMC_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attn_small_bwd_kernel<E, 32><<<ceil_div(npairs, ppc), threads, sm, st>>>(npairs, T, h, dh, ppc, qkv, dout, dqkv, 1.f / sqrtf((float)dh));
+      AMC_CUDA(cudaFuncSetAttribute(attn_frames_bwd_kernel<E, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attn_frames_bwd_kernel<E, 32><<<grid, threads, sm, st>>>(B, T, h, dh, F, qkv, dout, dqkv, sc);
     }
     AMC_LAUNCH_CHECK();
     return 0;
