@@ -406,8 +406,7 @@ struct Model {
     GemmArgs g;
     // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
-                      G + L.be2, drop, site_ffn(l), st));
-    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, d, (const E*)w.dw16, d, G + L.b2, st));
+                      G + L.be2, G + L.b2, drop, site_ffn(l), st));
     AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2));
     // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
     g = GemmArgs();
@@ -428,8 +427,7 @@ struct Model {
     AMC_TRY(gemm<E>(g, st));
     // norm1 backward
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
-                      G + L.be1, drop, site_attn(l), st));
-    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, d, (const E*)w.du16, d, G + L.bo, st));
+                      G + L.be1, G + L.bo, drop, site_attn(l), st));
     AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo));
     g = GemmArgs();
     g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
@@ -633,9 +631,9 @@ int amc_layernorm_bwd(int dtype, int M, int d, const float* dy, const void* xhat
   AMC_CHECK_ARG(dy && xhat && rstd && gamma, "NULL argument");
   DropoutCfg nodrop = make_dropout(0.f, 0, 0, false);
   if (dtype == AMC_BF16)
-    return ln_bwd<bf16>(M, d, dy, (const bf16*)xhat, rstd, gamma, (bf16*)du16, du32, dgamma, dbeta, nodrop, 0,
+    return ln_bwd<bf16>(M, d, dy, (const bf16*)xhat, rstd, gamma, (bf16*)du16, du32, dgamma, dbeta, nullptr, nodrop, 0,
                         (cudaStream_t)stream);
-  return ln_bwd<float>(M, d, dy, (const float*)xhat, rstd, gamma, (float*)du16, du32, dgamma, dbeta, nodrop, 0,
+  return ln_bwd<float>(M, d, dy, (const float*)xhat, rstd, gamma, (float*)du16, du32, dgamma, dbeta, nullptr, nodrop, 0,
                        (cudaStream_t)stream);
 }
 

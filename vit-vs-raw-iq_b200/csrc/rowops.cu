@@ -137,6 +137,111 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(int M, int d, const float* 
   }
 }
 
+// Vectorised LayerNorm backward for d % 8 == 0: each lane owns 8 consecutive columns per 256-column
+// group (32-byte fp32 / 16-byte bf16 accesses, a whole row is one contiguous warp transaction).  Besides
+// dgamma/dbeta it also accumulates the column sums of the (dropout-masked) du16 it writes, i.e. the bias
+// gradient of the sub-layer's output projection (Appendix B: db = sum d_out), saving a pass over du16.
+template <typename E, int G>   // G = number of 256-column groups (d <= 256*G)
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(int M, int d, const float* __restrict__ dy,
+                                                         const E* __restrict__ xhat, const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, E* __restrict__ du16,
+                                                         float* __restrict__ du32, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                         DropoutCfg drop, uint32_t site) {
+  __shared__ float red[3][8][G * 256 / 8 + 1];   // [acc][warp][column slot] -- reduced 8 columns at a time below
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float g[G][8], ag[G][8], ab[G][8], ad[G][8];
+  bool on[G];
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    const int c0 = k * 256 + lane * 8;
+    on[k] = c0 < d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[k][j] = on[k] ? __ldg(gamma + c0 + j) : 0.f;
+      ag[k][j] = 0.f; ab[k][j] = 0.f; ad[k][j] = 0.f;
+    }
+  }
+  const float inv_d = 1.f / (float)d;
+  for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
+    const size_t base = (size_t)row * d;
+    float dyv[G][8], xh[G][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      if (on[k]) {
+        const int c0 = k * 256 + lane * 8;
+        const float4 a = *reinterpret_cast<const float4*>(dy + base + c0);
+        const float4 b = *reinterpret_cast<const float4*>(dy + base + c0 + 4);
+        const float4 x0 = load4(xhat + base + c0), x1 = load4(xhat + base + c0 + 4);
+        dyv[k][0] = a.x; dyv[k][1] = a.y; dyv[k][2] = a.z; dyv[k][3] = a.w;
+        dyv[k][4] = b.x; dyv[k][5] = b.y; dyv[k][6] = b.z; dyv[k][7] = b.w;
+        xh[k][0] = x0.x; xh[k][1] = x0.y; xh[k][2] = x0.z; xh[k][3] = x0.w;
+        xh[k][4] = x1.x; xh[k][5] = x1.y; xh[k][6] = x1.z; xh[k][7] = x1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dyv[k][j] = 0.f; xh[k][j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = dyv[k][j] * g[k][j];
+        s1 += gg;
+        s2 = fmaf(gg, xh[k][j], s2);
+        ag[k][j] = fmaf(dyv[k][j], xh[k][j], ag[k][j]);
+        ab[k][j] += dyv[k][j];
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+    const float rs = rstd[row];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      if (!on[k]) continue;
+      const int c0 = k * 256 + lane * 8;
+      float du[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) du[j] = rs * (dyv[k][j] * g[k][j] - s1 - xh[k][j] * s2);
+      if (du32) {
+        *reinterpret_cast<float4*>(du32 + base + c0) = make_float4(du[0], du[1], du[2], du[3]);
+        *reinterpret_cast<float4*>(du32 + base + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
+      }
+      if (drop.p > 0.f) {
+        const float4 m0 = dropout_mult4(drop, site, (uint64_t)(base + c0) >> 2);
+        const float4 m1 = dropout_mult4(drop, site, ((uint64_t)(base + c0) >> 2) + 1);
+        du[0] *= m0.x; du[1] *= m0.y; du[2] *= m0.z; du[3] *= m0.w;
+        du[4] *= m1.x; du[5] *= m1.y; du[6] *= m1.z; du[7] *= m1.w;
+      }
+      if (du16) {
+        store4(du16 + base + c0, make_float4(du[0], du[1], du[2], du[3]));
+        store4(du16 + base + c0 + 4, make_float4(du[4], du[5], du[6], du[7]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ad[k][j] += du[j];
+    }
+  }
+  // block reduction (8 warps) then one atomic per column per block
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __syncthreads();
+      red[0][warp][lane] = ag[k][j];
+      red[1][warp][lane] = ab[k][j];
+      red[2][warp][lane] = ad[k][j];
+      __syncthreads();
+      if (warp < 3) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w) t += red[warp][w][lane];
+        const int c = k * 256 + lane * 8 + j;
+        if (c < d) {
+          float* dst = warp == 0 ? dgamma : (warp == 1 ? dbeta : dbias);
+          if (dst) atomicAdd(dst + c, t);
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Column sums: out[n] += sum_m X[m, n]   (bias gradients: Appendix B "db = sum dY")
 // ---------------------------------------------------------------------------------------
@@ -549,21 +654,6 @@ template int ln_fwd<bf16>(int, int, const float*, const float*, const float*, fl
                           cudaStream_t);
 
 template <typename E>
-int ln_bwd(int M, int d, const float* dy, const E* xhat, const float* rstd, const float* gamma, E* du16,
-           float* du32, float* dgamma, float* dbeta, const DropoutCfg& drop, uint32_t site, cudaStream_t st) {
-  AMC_CHECK_ARG(d >= 1 && d <= 32 * MAXV, "layernorm_bwd: d=%d unsupported (1..512)", d);
-  if (M == 0) return 0;
-  const int blocks = std::min(ceil_div(M, 8), 148 * 4);
-  ln_bwd_kernel<E><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, drop, site);
-  AMC_LAUNCH_CHECK();
-  return 0;
-}
-template int ln_bwd<float>(int, int, const float*, const float*, const float*, const float*, float*, float*,
-                           float*, float*, const DropoutCfg&, uint32_t, cudaStream_t);
-template int ln_bwd<bf16>(int, int, const float*, const bf16*, const float*, const float*, bf16*, float*, float*,
-                          float*, const DropoutCfg&, uint32_t, cudaStream_t);
-
-template <typename E>
 int colsum(int M, int N, const E* X, int ld, float* out, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
   const int cb = ceil_div(N, 32);
@@ -576,6 +666,36 @@ int colsum(int M, int N, const E* X, int ld, float* out, cudaStream_t st) {
 }
 template int colsum<float>(int, int, const float*, int, float*, cudaStream_t);
 template int colsum<bf16>(int, int, const bf16*, int, float*, cudaStream_t);
+
+template <typename E>
+int ln_bwd(int M, int d, const float* dy, const E* xhat, const float* rstd, const float* gamma, E* du16,
+           float* du32, float* dgamma, float* dbeta, float* dbias, const DropoutCfg& drop, uint32_t site,
+           cudaStream_t st) {
+  AMC_CHECK_ARG(d >= 1 && d <= 32 * MAXV, "layernorm_bwd: d=%d unsupported (1..512)", d);
+  if (M == 0) return 0;
+  auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+  if (d % 8 == 0 && al(dy, 16) && al(xhat, 16) && al(du16, 16) && al(du32, 16)) {
+    const int blocks = std::min(ceil_div(M, 8), 148 * 3);
+    if (d <= 256)
+      ln_bwd_vec_kernel<E, 1><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, dbias,
+                                                      drop, site);
+    else
+      ln_bwd_vec_kernel<E, 2><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, dbias,
+                                                      drop, site);
+    AMC_LAUNCH_CHECK();
+    return 0;
+  }
+  const int blocks = std::min(ceil_div(M, 8), 148 * 4);
+  ln_bwd_kernel<E><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, drop, site);
+  AMC_LAUNCH_CHECK();
+  if (dbias && du16) AMC_TRY(colsum<E>(M, d, du16, d, dbias, st));
+  return 0;
+}
+template int ln_bwd<float>(int, int, const float*, const float*, const float*, const float*, float*, float*,
+                           float*, float*, float*, const DropoutCfg&, uint32_t, cudaStream_t);
+template int ln_bwd<bf16>(int, int, const float*, const bf16*, const float*, const float*, bf16*, float*, float*,
+                          float*, float*, const DropoutCfg&, uint32_t, cudaStream_t);
+
 
 static PatchP make_patchp(const AmcDesc& D, int Ttok, int K) {
   PatchP p;

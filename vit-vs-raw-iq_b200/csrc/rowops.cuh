@@ -22,7 +22,8 @@ int ln_fwd(int M, int d, const float* u, const float* gamma, const float* beta, 
            E* xhat, float* rstd, cudaStream_t st);
 template <typename E>
 int ln_bwd(int M, int d, const float* dy, const E* xhat, const float* rstd, const float* gamma, E* du16,
-           float* du32, float* dgamma, float* dbeta, const DropoutCfg& drop, uint32_t site, cudaStream_t st);
+           float* du32, float* dgamma, float* dbeta, float* dbias /* += column sums of du16, nullable */,
+           const DropoutCfg& drop, uint32_t site, cudaStream_t st);
 template <typename E>
 int colsum(int M, int N, const E* X, int ld, float* out, cudaStream_t st);
 template <typename E>
