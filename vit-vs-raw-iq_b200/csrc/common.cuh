@@ -102,22 +102,28 @@ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool tra
   c.off_hi = (uint32_t)(offset >> 32);
   return c;
 }
-// 64-bit counter hash (splitmix64 finaliser): 64 random bits per group of 4 elements, 16 bits each.
-// Cheap enough (~4 integer instructions per element) to sit in a GEMM epilogue that must keep up with
-// tcgen05; dropout only needs an unbiased, well-mixed keep decision per element.
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+// Two 32-bit counter hashes (murmur3 finaliser over an affine function of the element-group index) give
+// 64 random bits per group of 4 elements, 16 bits each.  ~5 integer instructions per element: cheap enough
+// to sit in a GEMM epilogue that has to keep up with tcgen05; dropout only needs an unbiased, well-mixed
+// keep decision per element.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
 // keep-multipliers (0 or scale) for elements [4*q4, 4*q4+4) of dropout site `site`
 __device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint32_t site, uint64_t q4) {
-  const uint64_t key = ((uint64_t)c.seed_hi << 32 | c.seed_lo) ^ (((uint64_t)c.off_hi << 32 | c.off_lo) * 0x9E3779B97F4A7C15ull) ^
-                       ((uint64_t)site << 56);
-  const uint64_t r = mix64(mix64(q4 + key) ^ key);
+  const uint32_t k0 = c.seed_lo ^ (c.off_lo * 0x9E3779B9u) ^ (site * 0x85EBCA6Bu);          // loop-invariant
+  const uint32_t k1 = c.seed_hi ^ (c.off_hi * 0x7FEB352Du) ^ (c.off_lo * 0xC2B2AE35u) ^ (site * 0x27D4EB2Fu) ^ 0x165667B1u;
+  const uint32_t lo = (uint32_t)q4, hi = (uint32_t)(q4 >> 32);
+  const uint32_t a = fmix32(lo * 0x9E3779B1u + hi * 0x7FEB352Du + k0);
+  const uint32_t b = fmix32((lo ^ 0x68E31DA4u) * 0xB5297A4Du + hi * 0x1B873593u + k1);
   const uint32_t t16 = c.thresh >> 16;
-  return make_float4((uint32_t)(r & 0xFFFF) >= t16 ? c.scale : 0.f, (uint32_t)((r >> 16) & 0xFFFF) >= t16 ? c.scale : 0.f,
-                     (uint32_t)((r >> 32) & 0xFFFF) >= t16 ? c.scale : 0.f, (uint32_t)(r >> 48) >= t16 ? c.scale : 0.f);
+  return make_float4((a & 0xFFFFu) >= t16 ? c.scale : 0.f, (a >> 16) >= t16 ? c.scale : 0.f,
+                     (b & 0xFFFFu) >= t16 ? c.scale : 0.f, (b >> 16) >= t16 ? c.scale : 0.f);
 }
 // dropout sites (layer l): 0 = after positional encoding (encoder.py:111);
 // 1+3l = after attention out-proj (encoder_layer.py:24); 2+3l = FFN hidden (position_wise_feed_forward.py:15);

@@ -367,16 +367,22 @@ struct RowParams {
   int has_xhat;
 };
 
-template <int BN> struct RowCfg {
+template <int BN, int RE> struct RowCfg {
   static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
-  static constexpr int EPW = 16384;                        // epilogue bytes per warp
+  // bf16-output epilogues are instruction-heavy (dropout hash, mask tests, packing): two warps per TMEM
+  // lane quadrant alternate over the 32-column chunks; the fp32 / LayerNorm epilogues keep one warp per
+  // quadrant (the row statistics stay thread-local).
+  static constexpr int NEPI = (RE == RE_BF16 || RE == RE_MASK) ? 8 : 4;
+  static constexpr int EPW = (NEPI == 8) ? 8192 : 16384;   // epilogue bytes per warp
+  static constexpr int IN_STRIDE = (NEPI == 8) ? 2048 : 4096;
+  static constexpr int OUT_OFF = (NEPI == 8) ? 4096 : 8192;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + 4 * EPW;
-  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr int BAR_OFF = EPI_OFF + NEPI * EPW;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int THREADS = 64 + 32 * NEPI;
 };
-constexpr int ROW_THREADS = 192;
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
@@ -414,12 +420,12 @@ __device__ __forceinline__ uint32_t slab16_addr(uint32_t base, int row, int chun
 }
 
 template <int BN, int RE>
-__global__ void __launch_bounds__(ROW_THREADS, 1)
+__global__ void __launch_bounds__((RowCfg<BN, RE>::THREADS), 1)
 gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapO16,
                    const __grid_constant__ CUtensorMap mapO32, const __grid_constant__ CUtensorMap mapXh,
                    const TcParams p, const RowParams rp) {
-  using C = RowCfg<BN>;
+  using C = RowCfg<BN, RE>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                          ~(uintptr_t)1023);
@@ -427,8 +433,8 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* in_bar = tempty_bar + 2;               // [4 warps][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 8);
+  uint64_t* in_bar = tempty_bar + 2;               // [NEPI warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 2 * C::NEPI);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
@@ -442,9 +448,9 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s, 1);
-      mbar_init(tempty_bar + s, 4);
+      mbar_init(tempty_bar + s, C::NEPI);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(in_bar + s, 1);
+    for (int s = 0; s < 2 * C::NEPI; ++s) mbar_init(in_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -461,25 +467,40 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ===================== epilogue: thread = accumulator row =====================
     constexpr bool HAS_IN = (RE != RE_BF16);
     constexpr int IN_BYTES = (RE == RE_MASK) ? 2048 : 4096;
-    const int ew = warp - 2, quad = warp & 3;
-    const uint32_t ebase = smem_u32(smem + C::EPI_OFF + ew * C::EPW);
+    constexpr int NSPLIT = C::NEPI / 4;               // warps sharing one lane quadrant
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    unsigned char* egen = smem + C::EPI_OFF + ew * C::EPW;
+    const uint32_t ebase = smem_u32(egen);
     uint64_t* my_in_bar = in_bar + ew * 2;
     const int nchunks_full = BN / 32;
     uint32_t g = 0;                                   // running chunk counter (input double buffer + phases)
     int as = 0;
     uint32_t aphase = 0;
-    // first input slab of the first tile
-    if (HAS_IN && lane == 0 && (int)blockIdx.x < total_tiles) {
-      const int tn = blockIdx.x % p.tiles_n, tm = blockIdx.x / p.tiles_n;
-      mbar_expect_tx(my_in_bar, IN_BYTES);
-      tma_load_2d(&mapIn, my_in_bar, smem + C::EPI_OFF + ew * C::EPW, tn * BN, tm * BM + quad * 32);
+    // (tile, chunk) this warp processes next, starting the search at (t, c); false when there is none
+    auto next_chunk = [&](int& t, int& c) -> bool {
+      while (t < total_tiles) {
+        const int nc = min(nchunks_full, (p.N - (t % p.tiles_n) * BN) >> 5);
+        if (c < nc) return true;
+        t += gridDim.x;
+        c = half;
+      }
+      return false;
+    };
+    auto issue_in = [&](int t, int c, uint32_t gi) {
+      uint64_t* nb = my_in_bar + (gi & 1);
+      mbar_expect_tx(nb, IN_BYTES);
+      tma_load_2d(&mapIn, nb, egen + (gi & 1) * C::IN_STRIDE, (t % p.tiles_n) * BN + c * 32,
+                  (t / p.tiles_n) * BM + quad * 32);
+    };
+    if (HAS_IN && lane == 0) {                        // first input slab
+      int t = blockIdx.x, c = half;
+      if (next_chunk(t, c)) issue_in(t, c, 0);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
       const int m_slab = tm * BM + quad * 32, m = m_slab + lane;
       const int n0 = tn * BN;
       const int nchunks = min(nchunks_full, (p.N - n0) >> 5);
-      const int next_tile = tile + gridDim.x;
       mbar_wait(tfull_bar + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
@@ -487,25 +508,20 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
       // ---------------- pass A: finish the accumulator (bias, dropout, mask, residual) -------------
 #pragma unroll 1
-      for (int ci = 0; ci < nchunks; ++ci, ++g) {
+      for (int ci = half; ci < nchunks; ci += NSPLIT, ++g) {
         const int n = n0 + ci * 32;
         uint32_t r[32];
         tmem_ld32(taddr + ci * 32, r);
+        float4 bv[8];
+        if (RE != RE_MASK && rp.bias) {               // issue the bias loads before waiting on TMEM
+#pragma unroll
+          for (int k = 0; k < 8; ++k) bv[k] = __ldg(reinterpret_cast<const float4*>(rp.bias + n) + k);
+        }
         if (HAS_IN) {
-          // prefetch the next input slab (next chunk, or first chunk of this CTA's next tile)
+          // prefetch this warp's next input slab (same tile, or the first chunk of its next tile)
           if (lane == 0) {
-            int nn = n + 32, mm = m_slab;
-            bool more = ci + 1 < nchunks;
-            if (!more && next_tile < total_tiles) {
-              nn = (next_tile % p.tiles_n) * BN;
-              mm = (next_tile / p.tiles_n) * BM + quad * 32;
-              more = true;
-            }
-            if (more) {
-              uint64_t* nb = my_in_bar + ((g + 1) & 1);
-              mbar_expect_tx(nb, IN_BYTES);
-              tma_load_2d(&mapIn, nb, smem + C::EPI_OFF + ew * C::EPW + ((g + 1) & 1) * 4096, nn, mm);
-            }
+            int t = tile, c = ci + NSPLIT;
+            if (next_chunk(t, c)) issue_in(t, c, g + 1);
           }
           mbar_wait(my_in_bar + (g & 1), (g >> 1) & 1);
         }
@@ -516,8 +532,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (RE != RE_MASK && rp.bias) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(rp.bias + n) + k);
-            v[4 * k] += b.x; v[4 * k + 1] += b.y; v[4 * k + 2] += b.z; v[4 * k + 3] += b.w;
+            v[4 * k] += bv[k].x; v[4 * k + 1] += bv[k].y; v[4 * k + 2] += bv[k].z; v[4 * k + 3] += bv[k].w;
           }
         }
         if (RE == RE_BF16 && rp.relu) {
@@ -533,7 +548,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         }
         if (RE == RE_MASK) {
-          const uint32_t ib = ebase + (g & 1) * 4096;
+          const uint32_t ib = ebase + (g & 1) * C::IN_STRIDE;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint32_t w0, w1, w2, w3;
@@ -552,7 +567,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         }
         if (RE == RE_RES32 || RE == RE_LN) {
-          const uint32_t ib = ebase + (g & 1) * 4096;
+          const uint32_t ib = ebase + (g & 1) * C::IN_STRIDE;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 q = lds128(slab32_addr(ib, lane, k));
@@ -569,7 +584,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tmem_st32(taddr + ci * 32, w);              // park u in TMEM for the statistics passes
           __syncwarp();
         } else if (RE == RE_RES32) {
-          const uint32_t ob = ebase + 8192 + (g & 1) * 4096;
+          const uint32_t ob = ebase + C::OUT_OFF + (g & 1) * 4096;
           if (lane == 0) bulk_wait_read<1>();         // the store that last used this buffer has read it
           __syncwarp();
 #pragma unroll
@@ -583,7 +598,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             bulk_commit();
           }
         } else {
-          const uint32_t ob = ebase + 8192 + (g & 1) * 2048;
+          const uint32_t ob = ebase + C::OUT_OFF + (g & 1) * 2048;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
 #pragma unroll
@@ -766,7 +781,7 @@ int launch(const GemmArgs& g, cudaStream_t st) {
 
 template <int BN, int RE>
 int launch_row(const GemmArgs& g, cudaStream_t st) {
-  using C = RowCfg<BN>;
+  using C = RowCfg<BN, RE>;
   const Epi& e = g.epi;
   CUtensorMap mapA, mapB, mapIn, mapO16, mapO32, mapXh;
   AMC_TRY(make_map(&mapA, g.A, g.M, g.K, g.lda, BK, BM));
@@ -794,7 +809,7 @@ int launch_row(const GemmArgs& g, cudaStream_t st) {
   const int grid = (int)std::min<long long>(tiles, num_sms());
   auto kern = gemm_tc_row_kernel<BN, RE>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  kern<<<grid, ROW_THREADS, C::SMEM_BYTES, st>>>(mapA, mapB, mapIn, mapO16, mapO32, mapXh, p, rp);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mapA, mapB, mapIn, mapO16, mapO32, mapXh, p, rp);
   AMC_LAUNCH_CHECK();
   return 0;
 }
