@@ -377,8 +377,11 @@ struct Model {
 
   // ---- backward ---------------------------------------------------------------------------
   // weight-gradient GEMM: dW[No, Ki] += dY[M, No]^T X[M, Ki]
-  int wgrad(int No, int Ki, const void* dY, int ldy, const void* X, int ldx, float* dW) {
+  // ... and db[No] += column sums of dY: inside the same kernel on the bf16 path, a colsum launch in fp32
+  int wgrad(int No, int Ki, const void* dY, int ldy, const void* X, int ldx, float* dW, float* db) {
+    if (db && sizeof(E) != 2) AMC_PROF("colsum", 0.0, 0.0, colsum<E>((int)m.M, No, (const E*)dY, ldy, db, st));
     GemmArgs g;
+    if (sizeof(E) == 2) g.epi.colsum_out = db;
     g.M = No; g.N = Ki; g.K = (int)m.M;
     g.A = dY; g.lda = ldy; g.transA = 1;
     g.B = X; g.ldb = ldx; g.transB = 1;
@@ -406,8 +409,8 @@ struct Model {
     GemmArgs g;
     // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
-                      G + L.be2, G + L.b2, drop, site_ffn(l), st));
-    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2));
+                      G + L.be2, nullptr, drop, site_ffn(l), st));
+    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2, G + L.b2));
     // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
     g = GemmArgs();
     g.M = M; g.N = F; g.K = d; g.A = w.dw16; g.lda = d;
@@ -416,8 +419,7 @@ struct Model {
     g.epi.mask_src = b.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
     g.epi.D16 = w.da; g.epi.ldd16 = F;
     AMC_TRY(gemm<E>(g, st));
-    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, F, (const E*)w.da, F, G + L.b1, st));
-    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1));
+    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1, G + L.b1));
     // dgrad FFN1 + skip -> gradient w.r.t. x1
     g = GemmArgs();
     g.M = M; g.N = d; g.K = F; g.A = w.da; g.lda = F;
@@ -427,8 +429,8 @@ struct Model {
     AMC_TRY(gemm<E>(g, st));
     // norm1 backward
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
-                      G + L.be1, G + L.bo, drop, site_attn(l), st));
-    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo));
+                      G + L.be1, nullptr, drop, site_attn(l), st));
+    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo, G + L.bo));
     g = GemmArgs();
     g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
     dgrad_operand(g, l, L.wo, 3 * dd, d, d);
@@ -439,8 +441,7 @@ struct Model {
       ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
       AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, st));
     }
-    AMC_PROF("colsum", 0.0, 0.0, colsum<E>(M, 3 * d, (const E*)w.dqkv, 3 * d, G + L.bq, st));
-    AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq));
+    AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq, G + L.bq));
     // dgrad QKV + skip -> gradient w.r.t. the layer input
     g = GemmArgs();
     g.M = M; g.N = d; g.K = 3 * d; g.A = w.dqkv; g.lda = 3 * d;
@@ -478,8 +479,9 @@ struct Model {
         if (m.has_cls) AMC_PROF("frontend_bwd_misc", 0.0, 0.0, cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
         AMC_PROF("frontend_bwd_misc", 0.0, 0.0, gather_tok_rows<E>(m.B, m.T, m.Ttok, m.d, m.has_cls, w.dy32, (E*)w.demb, drop, st));
         const int Mt = m.B * m.Ttok;
-        AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
+        if (sizeof(E) != 2) AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
         GemmArgs g;
+        if (sizeof(E) == 2) g.epi.colsum_out = grads + L.emb_b;
         g.M = m.d; g.N = m.K; g.K = Mt;
         g.A = w.demb; g.lda = m.d; g.transA = 1;
         g.B = w.Apatch; g.ldb = m.K; g.transB = 1;

@@ -24,6 +24,9 @@ struct Epi {
   float* D32 = nullptr;
   int ldd32 = 0;
   int accumulate = 0;             // D32 += (atomic)
+  // weight-gradient GEMMs (token-major operands): colsum_out[m] += sum_k A[k, m], i.e. the bias gradient of the
+  // same layer, summed from the A tiles while they sit in shared memory (bf16 tcgen05 path only)
+  float* colsum_out = nullptr;
   // fused LayerNorm over the row (bf16 tcgen05 path, N <= 256): u = epilogue value, y = gamma*xhat+beta ->
   // D16 (bf16 y), D32 (fp32 y), ln_xhat (bf16, optional, pitch N), ln_rstd (fp32 [M], optional)
   const float* ln_gamma = nullptr;

@@ -153,7 +153,8 @@ template <int BN> struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered accumulator
   static constexpr int STG_BYTES = NEPI_WARPS * 32 * STG_LD * 4;   // per-epilogue-warp transpose tiles
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
+  static constexpr int AUX_BYTES = 1024;                   // barriers, TMEM slot, bias-gradient reduction buffer
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + AUX_BYTES + STG_BYTES;
 };
 
 struct TcParams {
@@ -255,7 +256,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  float* sred = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);      // [128]
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::AUX_BYTES);
+  const bool do_cs = (MODE_MN == 1) && epi.colsum_out != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, do_cs ? 1 + NEPI_WARPS : 1);   // MMA commit (+ the column-sum readers)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s, 1);
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) sred[threadIdx.x - 64] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -288,11 +292,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     int as = 0;
     uint32_t aphase = 0;
+    int cs_stage = 0;
+    uint32_t cs_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
       const int tn = mn % p.tiles_n, tm = mn / p.tiles_n;
       const int m_base = tm * BM + quad * 32;
       const int n0 = tn * BN;
+      if (MODE_MN == 1 && do_cs) {
+        // Bias gradient for free: while the MMAs consume a stage, the (otherwise idle) epilogue warps add up
+        // the columns of its A tile (the gradient matrix, [64 tokens][128 outputs], 128B-swizzled rows).
+        // Only the first N tile of each M block does the sums; every warp still releases every stage.
+        const int split = tile % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const bool mine = (tn == 0);
+        const int et = threadIdx.x - 64;              // 0..255
+        const int q = et & 15, grp = et >> 4;         // 16-byte chunk of the 128 columns, group of 4 tokens
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + cs_stage, cs_phase);
+          if (mine) {
+            const uint32_t sa = smem_u32(smem + cs_stage * C::STAGE_BYTES) + (uint32_t)(q >> 3) * 8192u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int k = grp * 4 + t;
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(sa + (uint32_t)k * 128u + (uint32_t)(((q & 7) ^ (k & 7)) << 4)));
+              acc[0] += __uint_as_float(w0 << 16); acc[1] += __uint_as_float(w0 & 0xFFFF0000u);
+              acc[2] += __uint_as_float(w1 << 16); acc[3] += __uint_as_float(w1 & 0xFFFF0000u);
+              acc[4] += __uint_as_float(w2 << 16); acc[5] += __uint_as_float(w2 & 0xFFFF0000u);
+              acc[6] += __uint_as_float(w3 << 16); acc[7] += __uint_as_float(w3 & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar + cs_stage);
+          if (++cs_stage == C::STAGES) { cs_stage = 0; cs_phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(sred + q * 8 + j, acc[j]);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et < 128) {
+            const float v = sred[et];
+            sred[et] = 0.f;
+            const int mrow = tm * BM + et;
+            if (mrow < p.M && v != 0.f) atomicAdd(epi.colsum_out + mrow, v);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       mbar_wait(tfull_bar + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);

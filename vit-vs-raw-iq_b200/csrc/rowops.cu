@@ -479,7 +479,9 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(int B, int T, int d,
 }
 
 // head backward, part 2: dW[k,:] += sum_b dlogits[b,k] hl[b,:] ; db[k] += sum_b dlogits[b,k]
-// and (head_ln) dlnw += sum_b dhl*xhat ; dlnb += sum_b dhl.   grid (C+1, chunks); blockDim = 128
+// and (head_ln) dlnw += sum_b dhl*xhat ; dlnb += sum_b dhl.
+// grid (ceil(d/128), frame chunks); one thread per column keeps a register accumulator per class, so
+// hl is read exactly once and dlogits rows are warp-uniform (broadcast) loads.
 __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int C, int head_ln,
                                                               const float* __restrict__ dlogits,
                                                               const float* __restrict__ s_hl,
@@ -487,22 +489,27 @@ __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int 
                                                               const float* __restrict__ s_xhat,
                                                               float* __restrict__ dW, float* __restrict__ dbias,
                                                               float* __restrict__ dlnw, float* __restrict__ dlnb) {
-  const int k = blockIdx.x;
+  constexpr int KG = 24;
+  const int c = blockIdx.x * 128 + threadIdx.x;
   const int per = (B + gridDim.y - 1) / gridDim.y;
   const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
-  if (k < C) {
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      float s = 0.f;
-      for (int b = b0; b < b1; ++b) s = fmaf(__ldg(dlogits + (size_t)b * C + k), s_hl[(size_t)b * d + c], s);
-      atomicAdd(dW + (size_t)k * d + c, s);
+  if (c < d) {
+    for (int k0 = 0; k0 < C; k0 += KG) {
+      float acc[KG];
+#pragma unroll
+      for (int k = 0; k < KG; ++k) acc[k] = 0.f;
+      for (int b = b0; b < b1; ++b) {
+        const float h = s_hl[(size_t)b * d + c];
+        const float* dl = dlogits + (size_t)b * C + k0;
+#pragma unroll
+        for (int k = 0; k < KG; ++k)
+          if (k0 + k < C) acc[k] = fmaf(__ldg(dl + k), h, acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < KG; ++k)
+        if (k0 + k < C) atomicAdd(dW + (size_t)(k0 + k) * d + c, acc[k]);
     }
-    if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int b = b0; b < b1; ++b) s += __ldg(dlogits + (size_t)b * C + k);
-      atomicAdd(dbias + k, s);
-    }
-  } else if (head_ln) {
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (head_ln) {
       float sg = 0.f, sb = 0.f;
       for (int b = b0; b < b1; ++b) {
         const float g = dhl[(size_t)b * d + c];
@@ -512,6 +519,11 @@ __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int 
       atomicAdd(dlnw + c, sg);
       atomicAdd(dlnb + c, sb);
     }
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < C) {
+    float sbias = 0.f;
+    for (int b = b0; b < b1; ++b) sbias += __ldg(dlogits + (size_t)b * C + threadIdx.x);
+    atomicAdd(dbias + threadIdx.x, sbias);
   }
 }
 
@@ -779,8 +791,8 @@ int head_bwd(int B, int T, int d, int C, int has_cls, int head_ln, const float* 
   head_bwd_rows_kernel<<<ceil_div(B, 4), 128, 0, st>>>(B, T, d, C, has_cls, head_ln, dlogits, W, lnw, s_xhat,
                                                        s_rstd, dxL, dhl_scratch);
   AMC_LAUNCH_CHECK();
-  const int chunks = std::max(1, std::min(ceil_div(B, 64), 32));
-  head_bwd_params_kernel<<<dim3(C + 1, chunks), 128, 0, st>>>(B, d, C, head_ln, dlogits, s_hl, dhl_scratch, s_xhat,
+  const int chunks = std::max(1, std::min(ceil_div(B, 64), 148));
+  head_bwd_params_kernel<<<dim3(ceil_div(d, 128), chunks), 128, 0, st>>>(B, d, C, head_ln, dlogits, s_hl, dhl_scratch, s_xhat,
                                                               dW, dbias, dlnw, dlnb);
   AMC_LAUNCH_CHECK();
   return 0;
