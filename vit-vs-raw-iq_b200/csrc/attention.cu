@@ -6,6 +6,8 @@
 // (row statistics, dQ), phase 2 is key-row parallel (dK, dV) -- no atomics, deterministic.
 #include "attention.cuh"
 
+#include <type_traits>
+
 namespace amc {
 namespace {
 
@@ -497,6 +499,311 @@ __global__ void __launch_bounds__(256) attn_frames_bwd_kernel(int B, int T, int 
   if (tid == 0) bulk_wait_all0();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant for T <= 16 tokens, bf16, head dim 16*KD (KD = 1, 2, 4): one WARP per (frame, head).
+// The 16x16 score tile is two m16n8k16 MMAs per 16 head-dim columns; operands come straight from the staged
+// frame rows with ldmatrix (row pitch 6d+16 bytes: the 8 rows of every 8x8 matrix hit 8 different 16-byte
+// bank groups).  Softmax runs on the accumulator fragments (quad shuffles); P and dS are re-used as A
+// fragments directly from registers, and go through a tiny per-warp smem tile only where the transpose is
+// needed (dK = dS^T Q, dV = P^T dO).  Rows/keys >= T are padding: their addresses are clamped to row T-1,
+// key columns are masked to -inf, query rows are zeroed in backward and never written.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// A-operand address (rows r0.., 16 columns at col0) / "K-pattern" B address (rows = n, cols = k) for lane
+__device__ __forceinline__ uint32_t addr_a(uint32_t base, int pitch_b, int T, int col0, int lane) {
+  const int r = min((lane & 7) + ((lane >> 3) & 1) * 8, T - 1);
+  return base + r * pitch_b + (col0 + (lane >> 4) * 8) * 2;
+}
+__device__ __forceinline__ uint32_t addr_bk(uint32_t base, int pitch_b, int T, int col0, int lane) {
+  const int r = min((lane & 7) + (lane >> 4) * 8, T - 1);
+  return base + r * pitch_b + (col0 + ((lane >> 3) & 1) * 8) * 2;
+}
+// "V-pattern" (transposed) B address: rows = k (tokens), cols = n (16 head-dim columns at col0)
+__device__ __forceinline__ uint32_t addr_bv(uint32_t base, int pitch_b, int T, int col0, int lane) {
+  const int r = min((lane & 7) + ((lane >> 3) & 1) * 8, T - 1);
+  return base + r * pitch_b + (col0 + (lane >> 4) * 8) * 2;
+}
+
+// scores -> probabilities on the accumulator fragments; returns nothing, p[nt][*] normalised, masked
+__device__ __forceinline__ void frag_softmax(float (&c)[2][4], int T, float scale, int lane) {
+  const int cb = (lane & 3) * 2;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = nt * 8 + cb + e < T;
+      c[nt][e] = ok ? c[nt][e] * scale : -INFINITY;
+      c[nt][2 + e] = ok ? c[nt][2 + e] * scale : -INFINITY;
+      m0 = fmaxf(m0, c[nt][e]);
+      m1 = fmaxf(m1, c[nt][2 + e]);
+    }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      c[nt][e] = __expf(c[nt][e] - m0);
+      c[nt][2 + e] = __expf(c[nt][2 + e] - m1);
+      s0 += c[nt][e];
+      s1 += c[nt][2 + e];
+    }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float i0 = 1.f / s0, i1 = 1.f / s1;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      c[nt][e] *= i0;
+      c[nt][2 + e] *= i1;
+    }
+}
+
+template <int KD>
+__global__ void __launch_bounds__(256) attn_mma_fwd_kernel(int B, int T, int h, int F, const bf16* __restrict__ qkv,
+                                                           bf16* __restrict__ out, float scale) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int dh = 16 * KD;
+  const int d = h * dh, ld = 3 * d;
+  const int s_in = ld + 8, s_out = d + 8;
+  const int pin = s_in * 2;                                        // row pitch in bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  bf16* blk0 = reinterpret_cast<bf16*>(smem_raw + 128);
+  const size_t in_elems = (size_t)F * T * s_in;
+  bf16* oblk = blk0 + 2 * in_elems;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  if (tid == 0) {
+    mbar_init1(bars);
+    mbar_init1(bars + 1);
+  }
+  __syncthreads();
+  const int stride_f = gridDim.x * F;
+  int f0 = blockIdx.x * F;
+  if (tid == 0 && f0 < B) bulk_rows_in(blk0, s_in, qkv + (size_t)f0 * T * ld, min(F, B - f0) * T, ld, bars);
+  for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
+    const int nf = min(F, B - f0);
+    bf16* blk = blk0 + (it & 1) * in_elems;
+    if (tid == 0) {
+      const int fn = f0 + stride_f;
+      if (fn < B) bulk_rows_in(blk0 + ((it + 1) & 1) * in_elems, s_in, qkv + (size_t)fn * T * ld, min(F, B - fn) * T, ld,
+                               bars + ((it + 1) & 1));
+      bulk_wait_read0();                       // previous iteration's output rows have left oblk
+    }
+    mbar_wait_parity(bars + (it & 1), (it >> 1) & 1);
+    __syncthreads();
+    for (int pr = warp; pr < nf * h; pr += nw) {
+      const int f = pr / h, hh = pr - f * h;
+      const uint32_t qb = smem_addr(blk + (size_t)f * T * s_in + hh * dh);
+      const uint32_t kb = qb + d * 2, vb = qb + 2 * d * 2;
+      float c[2][4] = {};
+#pragma unroll
+      for (int ks = 0; ks < KD; ++ks) {
+        uint32_t a[4], b[4];
+        ldsm_x4(a, addr_a(qb, pin, T, ks * 16, lane));
+        ldsm_x4(b, addr_bk(kb, pin, T, ks * 16, lane));
+        mma_bf16(c[0], a, b[0], b[1]);
+        mma_bf16(c[1], a, b[2], b[3]);
+      }
+      frag_softmax(c, T, scale, lane);
+      uint32_t pa[4] = {pack2(c[0][0], c[0][1]), pack2(c[0][2], c[0][3]), pack2(c[1][0], c[1][1]),
+                        pack2(c[1][2], c[1][3])};
+      float o[2 * KD][4] = {};
+#pragma unroll
+      for (int np = 0; np < KD; ++np) {
+        uint32_t b[4];
+        ldsm_x4_t(b, addr_bv(vb, pin, T, np * 16, lane));
+        mma_bf16(o[2 * np], pa, b[0], b[1]);
+        mma_bf16(o[2 * np + 1], pa, b[2], b[3]);
+      }
+      const int g = lane >> 2, cb = (lane & 3) * 2;
+      bf16* ob = oblk + (size_t)f * T * s_out + hh * dh + cb;
+#pragma unroll
+      for (int nt = 0; nt < 2 * KD; ++nt) {
+        if (g < T) *reinterpret_cast<uint32_t*>(ob + (size_t)g * s_out + nt * 8) = pack2(o[nt][0], o[nt][1]);
+        if (g + 8 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)(g + 8) * s_out + nt * 8) = pack2(o[nt][2], o[nt][3]);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) bulk_rows_out(out + (size_t)f0 * T * d, oblk, s_out, nf * T, d);
+  }
+  if (tid == 0) bulk_wait_all0();
+}
+
+template <int KD>
+__global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, int F, const bf16* __restrict__ qkv,
+                                                           const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                                           float scale) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int dh = 16 * KD;
+  constexpr int TP = 24;                                            // pitch (elements) of the 16x16 transpose tiles
+  const int d = h * dh, ld = 3 * d;
+  const int s_in = ld + 8, s_do = d + 8;
+  const int pin = s_in * 2, pdo = s_do * 2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  bf16* blk = reinterpret_cast<bf16*>(smem_raw + 128);
+  bf16* doblk = blk + (size_t)F * T * s_in;
+  bf16* oblk = doblk + (size_t)F * T * s_do;
+  bf16* tiles = oblk + (size_t)F * T * s_in;                        // [warps][2][16][TP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  bf16* tP = tiles + (size_t)warp * 2 * 16 * TP;
+  bf16* tS = tP + 16 * TP;
+  if (tid == 0) mbar_init1(bar);
+  __syncthreads();
+  const int stride_f = gridDim.x * F;
+  int f0 = blockIdx.x * F;
+  auto issue = [&](int fs) {
+    const int rows = min(F, B - fs) * T;
+    mbar_expect(bar, (uint32_t)(rows * (ld + d) * 2));
+    for (int r = 0; r < rows; ++r) {
+      bulk_g2s(blk + (size_t)r * s_in, qkv + ((size_t)fs * T + r) * ld, (uint32_t)(ld * 2), bar);
+      bulk_g2s(doblk + (size_t)r * s_do, dout + ((size_t)fs * T + r) * d, (uint32_t)(d * 2), bar);
+    }
+  };
+  if (tid == 0 && f0 < B) issue(f0);
+  for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
+    const int nf = min(F, B - f0);
+    if (tid == 0) bulk_wait_read0();          // previous iteration's gradient rows have left oblk
+    mbar_wait_parity(bar, it & 1);
+    __syncthreads();
+    const int g = lane >> 2, cb = (lane & 3) * 2;
+    for (int pr = warp; pr < nf * h; pr += nw) {
+      const int f = pr / h, hh = pr - f * h;
+      const uint32_t qb = smem_addr(blk + (size_t)f * T * s_in + hh * dh);
+      const uint32_t kb = qb + d * 2, vb = qb + 2 * d * 2;
+      const uint32_t ob = smem_addr(doblk + (size_t)f * T * s_do + hh * dh);
+      float c[2][4] = {}, dp[2][4] = {};
+#pragma unroll
+      for (int ks = 0; ks < KD; ++ks) {
+        uint32_t a[4], b[4];
+        ldsm_x4(a, addr_a(qb, pin, T, ks * 16, lane));
+        ldsm_x4(b, addr_bk(kb, pin, T, ks * 16, lane));
+        mma_bf16(c[0], a, b[0], b[1]);
+        mma_bf16(c[1], a, b[2], b[3]);
+        ldsm_x4(a, addr_a(ob, pdo, T, ks * 16, lane));           // dO rows
+        ldsm_x4(b, addr_bk(vb, pin, T, ks * 16, lane));          // V^T: B[k=c][n=j] = V[j][c]
+        mma_bf16(dp[0], a, b[0], b[1]);
+        mma_bf16(dp[1], a, b[2], b[3]);
+      }
+      frag_softmax(c, T, scale, lane);
+      // delta_i = sum_j P dP ; dS = P (dP - delta) scale ; padded query rows are zeroed
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          d0 = fmaf(c[nt][e], dp[nt][e], d0);
+          d1 = fmaf(c[nt][2 + e], dp[nt][2 + e], d1);
+        }
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+      const bool r0 = g < T, r1 = g + 8 < T;
+      float ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          c[nt][e] = r0 ? c[nt][e] : 0.f;
+          c[nt][2 + e] = r1 ? c[nt][2 + e] : 0.f;
+          ds[nt][e] = r0 ? c[nt][e] * (dp[nt][e] - d0) * scale : 0.f;
+          ds[nt][2 + e] = r1 ? c[nt][2 + e] * (dp[nt][2 + e] - d1) * scale : 0.f;
+        }
+      uint32_t pa[4] = {pack2(c[0][0], c[0][1]), pack2(c[0][2], c[0][3]), pack2(c[1][0], c[1][1]),
+                        pack2(c[1][2], c[1][3])};
+      uint32_t sa[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
+                        pack2(ds[1][2], ds[1][3])};
+      // stage P and dS ([query][key], bf16) for the transposed products
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        *reinterpret_cast<uint32_t*>(tP + g * TP + nt * 8 + cb) = pa[2 * nt];
+        *reinterpret_cast<uint32_t*>(tP + (g + 8) * TP + nt * 8 + cb) = pa[2 * nt + 1];
+        *reinterpret_cast<uint32_t*>(tS + g * TP + nt * 8 + cb) = sa[2 * nt];
+        *reinterpret_cast<uint32_t*>(tS + (g + 8) * TP + nt * 8 + cb) = sa[2 * nt + 1];
+      }
+      __syncwarp();
+      uint32_t pta[4], sta[4];     // A fragments of P^T and dS^T: rows = keys, k = queries
+      {
+        const int r = (lane & 7) + (lane >> 4) * 8, cc = ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(pta, smem_addr(tP + r * TP + cc));
+        ldsm_x4_t(sta, smem_addr(tS + r * TP + cc));
+      }
+      bf16* og = oblk + (size_t)f * T * s_in + hh * dh + cb;
+#pragma unroll
+      for (int np = 0; np < KD; ++np) {
+        uint32_t bk_[4], bq_[4], bo_[4];
+        ldsm_x4_t(bk_, addr_bv(kb, pin, T, np * 16, lane));      // B[k=j][n=c] = K[j][c]
+        ldsm_x4_t(bq_, addr_bv(qb, pin, T, np * 16, lane));      // B[k=i][n=c] = Q[i][c]
+        ldsm_x4_t(bo_, addr_bv(ob, pdo, T, np * 16, lane));      // B[k=i][n=c] = dO[i][c]
+        float dq[2][4] = {}, dk[2][4] = {}, dv[2][4] = {};
+        mma_bf16(dq[0], sa, bk_[0], bk_[1]);
+        mma_bf16(dq[1], sa, bk_[2], bk_[3]);
+        mma_bf16(dk[0], sta, bq_[0], bq_[1]);
+        mma_bf16(dk[1], sta, bq_[2], bq_[3]);
+        mma_bf16(dv[0], pta, bo_[0], bo_[1]);
+        mma_bf16(dv[1], pta, bo_[2], bo_[3]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = np * 16 + u * 8;
+          if (r0) {
+            *reinterpret_cast<uint32_t*>(og + (size_t)g * s_in + col) = pack2(dq[u][0], dq[u][1]);
+            *reinterpret_cast<uint32_t*>(og + (size_t)g * s_in + d + col) = pack2(dk[u][0], dk[u][1]);
+            *reinterpret_cast<uint32_t*>(og + (size_t)g * s_in + 2 * d + col) = pack2(dv[u][0], dv[u][1]);
+          }
+          if (r1) {
+            *reinterpret_cast<uint32_t*>(og + (size_t)(g + 8) * s_in + col) = pack2(dq[u][2], dq[u][3]);
+            *reinterpret_cast<uint32_t*>(og + (size_t)(g + 8) * s_in + d + col) = pack2(dk[u][2], dk[u][3]);
+            *reinterpret_cast<uint32_t*>(og + (size_t)(g + 8) * s_in + 2 * d + col) = pack2(dv[u][2], dv[u][3]);
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();                          // all reads of q/k/v/dO done, all gradient rows staged
+    if (tid == 0) {
+      bulk_rows_out(dqkv + (size_t)f0 * T * ld, oblk, s_in, nf * T, ld);
+      const int fn = f0 + stride_f;
+      if (fn < B) issue(fn);
+    }
+  }
+  if (tid == 0) bulk_wait_all0();
+}
+
+inline bool use_mma(int T, int h, int dh) { return T <= 16 && (dh == 16 || dh == 32 || dh == 64) && (h * dh) % 8 == 0; }
+inline size_t mma_fwd_bytes(int T, int h, int dh, int F) {
+  const int d = h * dh;
+  return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2;
+}
+inline size_t mma_bwd_bytes(int T, int h, int dh, int F) {
+  const int d = h * dh;
+  return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2 + 8 * 2 * 16 * 24 * 2;
+}
+inline int mma_frames(int T, int h, int dh, bool bwd) {
+  int F = std::max(1, ceil_div(16, h));                 // at least ~2 pairs per warp
+  while (F < 8 && (bwd ? mma_bwd_bytes(T, h, dh, F + 1) : mma_fwd_bytes(T, h, dh, F + 1)) <= 100 * 1024) ++F;
+  return F;
+}
+
 // the frame kernels need 16-byte row copies: (3d, d) * sizeof(E) % 16 == 0
 template <typename E>
 inline bool use_small(int T, int h, int dh) {
@@ -530,6 +837,25 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
+  if constexpr (std::is_same<E, bf16>::value) {
+    if (use_mma(T, h, dh)) {
+      const int F = mma_frames(T, h, dh, false);
+      const size_t sm = mma_fwd_bytes(T, h, dh, F);
+      const int grid = std::min(ceil_div(B, F), 148 * 2);
+      const float sc = 1.f / sqrtf((float)dh);
+#define AMC_LAUNCH_MMA_FWD(KD)                                                                                      \
+  do {                                                                                                              \
+    AMC_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    attn_mma_fwd_kernel<KD><<<grid, 256, sm, st>>>(B, T, h, F, qkv, out, sc);                                       \
+  } while (0)
+      if (dh == 16) AMC_LAUNCH_MMA_FWD(1);
+      else if (dh == 32) AMC_LAUNCH_MMA_FWD(2);
+      else AMC_LAUNCH_MMA_FWD(4);
+#undef AMC_LAUNCH_MMA_FWD
+      AMC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (use_small<E>(T, h, dh)) {
     const int F = small_frames<E>(T, h, dh, small_fwd_bytes<E>);
     const size_t sm = small_fwd_bytes<E>(T, h, dh, F);
@@ -565,6 +891,25 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
+  if constexpr (std::is_same<E, bf16>::value) {
+    if (use_mma(T, h, dh)) {
+      const int F = mma_frames(T, h, dh, true);
+      const size_t sm = mma_bwd_bytes(T, h, dh, F);
+      const int grid = std::min(ceil_div(B, F), 148 * 2);
+      const float sc = 1.f / sqrtf((float)dh);
+#define AMC_LAUNCH_MMA_BWD(KD)                                                                                      \
+  do {                                                                                                              \
+    AMC_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    attn_mma_bwd_kernel<KD><<<grid, 256, sm, st>>>(B, T, h, F, qkv, dout, dqkv, sc);                                \
+  } while (0)
+      if (dh == 16) AMC_LAUNCH_MMA_BWD(1);
+      else if (dh == 32) AMC_LAUNCH_MMA_BWD(2);
+      else AMC_LAUNCH_MMA_BWD(4);
+#undef AMC_LAUNCH_MMA_BWD
+      AMC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (use_small<E>(T, h, dh)) {
     const int F = small_frames<E>(T, h, dh, small_bwd_bytes<E>);
     const size_t sm = small_bwd_bytes<E>(T, h, dh, F);
