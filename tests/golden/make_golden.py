@@ -137,9 +137,54 @@ def known_answers():
     assert (n1, n2) == (414859, 4748051)
 
 
+
+
+def trajectory_case():
+    """30 optimisation steps of the reference train loop (R/training/train.py:258-271) on a fixed synthetic
+    data set, dropout 0: per-step loss and accuracy, plus the final parameters.  Pins multi-step equivalence
+    (optimizer state, bias correction, clipping) of the fused TrainStep."""
+    AMC = import_reference("rawiq")
+    kw = dict(in_channels=2, seq_length=256, num_classes=4, d_model=32, n_head=4, n_layers=2, ffn_hidden=64,
+              drop_prob=0.0, device="cpu", use_cls_token=True, embedding_type="segment", segment_size=16)
+    torch.manual_seed(5)
+    model = AMC(**kw)
+    g = torch.Generator().manual_seed(11)
+    # 4 synthetic "modulations": different per-class amplitude patterns + noise (learnable in a few steps)
+    N, B = 256, 32
+    y = torch.randint(0, 4, (N,), generator=g)
+    base = torch.randn(4, 2, 256, generator=g)
+    X = base[y] * 0.8 + 0.6 * torch.randn(N, 2, 256, generator=g)
+    out = {"X": X.numpy(), "y": y.numpy()}
+    for k, v in model.state_dict().items():
+        out["param/" + k] = v.detach().numpy().copy()
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=1e-2, betas=(0.9, 0.99))
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+    losses, accs = [], []
+    model.train()
+    for it in range(30):
+        i = (it * B) % N
+        xb, yb = X[i:i + B], y[i:i + B]
+        opt.zero_grad()
+        o = model(xb)
+        loss = crit(o, yb)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        losses.append(loss.item())
+        accs.append((o.argmax(1) == yb).float().mean().item())
+    out["losses"] = np.array(losses, dtype=np.float64)
+    out["accs"] = np.array(accs, dtype=np.float64)
+    for n, p in model.named_parameters():
+        out["final/" + n] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "trajectory_rawiq.npz"), **out)
+    print("trajectory: loss %.4f -> %.4f, acc %.2f -> %.2f" % (losses[0], losses[-1], accs[0], accs[-1]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    for name, (kind, kw, B) in CASES.items():
-        run_case(name, kind, kw, B)
-    preprocessing_case()
-    known_answers()
+    if "--trajectory-only" not in sys.argv:
+        for name, (kind, kw, B) in CASES.items():
+            run_case(name, kind, kw, B)
+        preprocessing_case()
+        known_answers()
+    trajectory_case()

@@ -409,8 +409,8 @@ struct Model {
     GemmArgs g;
     // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
-                      G + L.be2, nullptr, drop, site_ffn(l), st));
-    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2, G + L.b2));
+                      G + L.be2, G + L.b2, drop, site_ffn(l), st));
+    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2, nullptr));
     // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
     g = GemmArgs();
     g.M = M; g.N = F; g.K = d; g.A = w.dw16; g.lda = d;
@@ -418,8 +418,10 @@ struct Model {
     g.name = "gemm_dgrad_ffn2";
     g.epi.mask_src = b.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
     g.epi.D16 = w.da; g.epi.ldd16 = F;
+    const bool fuse_db1 = sizeof(E) == 2 && F % 32 == 0 && F <= 2048;   // bias gradient summed in the mask epilogue
+    if (fuse_db1) g.epi.colsum_out = G + L.b1;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1, G + L.b1));
+    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1, fuse_db1 ? nullptr : G + L.b1));
     // dgrad FFN1 + skip -> gradient w.r.t. x1
     g = GemmArgs();
     g.M = M; g.N = d; g.K = F; g.A = w.da; g.lda = F;
@@ -429,8 +431,8 @@ struct Model {
     AMC_TRY(gemm<E>(g, st));
     // norm1 backward
     AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
-                      G + L.be1, nullptr, drop, site_attn(l), st));
-    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo, G + L.bo));
+                      G + L.be1, G + L.bo, drop, site_attn(l), st));
+    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo, nullptr));
     g = GemmArgs();
     g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
     dgrad_operand(g, l, L.wo, 3 * dd, d, d);
@@ -439,9 +441,9 @@ struct Model {
     AMC_TRY(gemm<E>(g, st));
     {
       ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
-      AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, st));
+      AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, G + L.bq, st));
     }
-    AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq, G + L.bq));
+    AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq, nullptr));
     // dgrad QKV + skip -> gradient w.r.t. the layer input
     g = GemmArgs();
     g.M = M; g.N = d; g.K = 3 * d; g.A = w.dqkv; g.lda = 3 * d;
@@ -617,8 +619,8 @@ int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, c
                       amc_stream_t stream) {
   AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
   if (dtype == AMC_BF16)
-    return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, (cudaStream_t)stream);
-  return attention_bwd<float>(B, T, h, dh, (const float*)qkv, (const float*)dout, (float*)dqkv, (cudaStream_t)stream);
+    return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, nullptr, (cudaStream_t)stream);
+  return attention_bwd<float>(B, T, h, dh, (const float*)qkv, (const float*)dout, (float*)dqkv, nullptr, (cudaStream_t)stream);
 }
 
 int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamma, const float* beta, float eps,

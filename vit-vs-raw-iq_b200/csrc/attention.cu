@@ -5,6 +5,7 @@
 // Backward recomputes P from Q,K (SURVEY Appendix B "what to save"): phase 1 is query-row parallel
 // (row statistics, dQ), phase 2 is key-row parallel (dK, dV) -- no atomics, deterministic.
 #include "attention.cuh"
+#include "rowops.cuh"
 
 #include <type_traits>
 
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(256) attn_mma_fwd_kernel(int B, int T, int h, 
 template <int KD>
 __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, int F, const bf16* __restrict__ qkv,
                                                            const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
-                                                           float scale) {
+                                                           float* __restrict__ dbias, float scale) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int dh = 16 * KD;
   constexpr int TP = 24;                                            // pitch (elements) of the 16x16 transpose tiles
@@ -681,6 +682,10 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, 
     }
   };
   if (tid == 0 && f0 < B) issue(f0);
+  // bias gradient of the QKV projection (Appendix B: db = sum of dQ|dK|dV rows): each thread owns up to two
+  // 4-column groups of the staged gradient rows and keeps their sums in registers across all its frames
+  float4 bsum[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+  const int ngroups = ld >> 2;
   for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
     const int nf = min(F, B - f0);
     if (tid == 0) bulk_wait_read0();          // previous iteration's gradient rows have left oblk
@@ -785,11 +790,36 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, 
       const int fn = f0 + stride_f;
       if (fn < B) issue(fn);
     }
+    if (dbias) {
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int gi = tid + sl * 256;
+        if (gi < ngroups)
+          for (int r = 0; r < nf * T; ++r) {
+            const float4 v = load4(oblk + (size_t)r * s_in + gi * 4);
+            bsum[sl].x += v.x; bsum[sl].y += v.y; bsum[sl].z += v.z; bsum[sl].w += v.w;
+          }
+      }
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int gi = tid + sl * 256;
+      if (gi < ngroups) {
+        atomicAdd(dbias + gi * 4 + 0, bsum[sl].x);
+        atomicAdd(dbias + gi * 4 + 1, bsum[sl].y);
+        atomicAdd(dbias + gi * 4 + 2, bsum[sl].z);
+        atomicAdd(dbias + gi * 4 + 3, bsum[sl].w);
+      }
+    }
   }
   if (tid == 0) bulk_wait_all0();
 }
 
-inline bool use_mma(int T, int h, int dh) { return T <= 16 && (dh == 16 || dh == 32 || dh == 64) && (h * dh) % 8 == 0; }
+inline bool use_mma(int T, int h, int dh) {
+  return T <= 16 && (dh == 16 || dh == 32 || dh == 64) && (h * dh) % 8 == 0 && 3 * h * dh <= 2048;
+}
 inline size_t mma_fwd_bytes(int T, int h, int dh, int F) {
   const int d = h * dh;
   return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2;
@@ -887,7 +917,9 @@ template int attention_fwd<float>(int, int, int, int, const float*, float*, cuda
 template int attention_fwd<bf16>(int, int, int, int, const bf16*, bf16*, cudaStream_t);
 
 template <typename E>
-int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, cudaStream_t st) {
+int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, bool* fused,
+                       cudaStream_t st) {
+  *fused = false;
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
@@ -900,13 +932,14 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
 #define AMC_LAUNCH_MMA_BWD(KD)                                                                                      \
   do {                                                                                                              \
     AMC_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    attn_mma_bwd_kernel<KD><<<grid, 256, sm, st>>>(B, T, h, F, qkv, dout, dqkv, sc);                                \
+    attn_mma_bwd_kernel<KD><<<grid, 256, sm, st>>>(B, T, h, F, qkv, dout, dqkv, dbias, sc);                         \
   } while (0)
       if (dh == 16) AMC_LAUNCH_MMA_BWD(1);
       else if (dh == 32) AMC_LAUNCH_MMA_BWD(2);
       else AMC_LAUNCH_MMA_BWD(4);
 #undef AMC_LAUNCH_MMA_BWD
       AMC_LAUNCH_CHECK();
+      *fused = true;
       return 0;
     }
   }
@@ -939,7 +972,16 @@ int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* d
   AMC_LAUNCH_CHECK();
   return 0;
 }
-template int attention_bwd<float>(int, int, int, int, const float*, const float*, float*, cudaStream_t);
-template int attention_bwd<bf16>(int, int, int, int, const bf16*, const bf16*, bf16*, cudaStream_t);
+// dbias (nullable): += column sums of dqkv, i.e. the gradient of the q/k/v biases.  The tensor-core kernel
+// produces it from its staged rows; the other kernels are followed by a column-sum pass.
+template <typename E>
+int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, cudaStream_t st) {
+  bool fused = false;
+  AMC_TRY(attention_bwd_impl<E>(B, T, h, dh, qkv, dout, dqkv, dbias, &fused, st));
+  if (dbias && !fused) AMC_TRY(colsum<E>(B * T, 3 * h * dh, dqkv, 3 * h * dh, dbias, st));
+  return 0;
+}
+template int attention_bwd<float>(int, int, int, int, const float*, const float*, float*, float*, cudaStream_t);
+template int attention_bwd<bf16>(int, int, int, int, const bf16*, const bf16*, bf16*, float*, cudaStream_t);
 
 }  // namespace amc

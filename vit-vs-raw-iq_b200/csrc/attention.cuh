@@ -9,5 +9,5 @@ namespace amc {
 template <typename E>
 int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_t st);
 template <typename E>
-int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, cudaStream_t st);
+int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, cudaStream_t st);
 }  // namespace amc

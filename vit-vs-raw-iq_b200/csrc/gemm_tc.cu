@@ -243,7 +243,10 @@ __device__ __forceinline__ void mma_loop(const TcParams& p, unsigned char* smem,
 // Kernel 1: generic epilogue (any flag combination, ragged N, split-K atomics).  The accumulator chunk
 // is transposed through shared memory so that global accesses are coalesced.
 // =================================================================================================
-template <int BN, int MODE_MN>
+// CS = 1 (weight-gradient mode only): also emit colsum_out[m] += sum_k A[k, m] from the staged A tiles.  It is a
+// compile-time switch: the extra shared-memory reads compete with the tensor core's operand fetches, and even the
+// dormant code path costs the main loop ~25 %, so the hot weight-gradient calls use CS = 0.
+template <int BN, int MODE_MN, int CS>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const TcParams p, const Epi epi) {
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sred = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);      // [128]
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::AUX_BYTES);
-  const bool do_cs = (MODE_MN == 1) && epi.colsum_out != nullptr;
+  constexpr bool do_cs = (MODE_MN == 1) && (CS == 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
@@ -416,6 +419,8 @@ struct RowParams {
   float ln_eps;
   float* rstd;
   int has_xhat;
+  float* colsum_out;   // RE_MASK / RE_BF16: += column sums of the values written (bias gradient of the producer layer)
+  int n_cols;          // N (size of the shared-memory column accumulator)
 };
 
 template <int BN, int RE> struct RowCfg {
@@ -430,7 +435,9 @@ template <int BN, int RE> struct RowCfg {
   static constexpr int OUT_OFF = (NEPI == 8) ? 4096 : 8192;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + NEPI * EPW;
-  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
+  static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), 8-warp variants
+  static constexpr int CS_BYTES = (NEPI == 8) ? 8192 : 0;
+  static constexpr int SMEM_BYTES = CS_OFF + CS_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int THREADS = 64 + 32 * NEPI;
 };
@@ -505,6 +512,10 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  float* sacc = reinterpret_cast<float*>(smem + C::CS_OFF);
+  const bool do_cs = C::CS_BYTES > 0 && rp.colsum_out != nullptr;
+  if (do_cs)
+    for (int i = threadIdx.x; i < rp.n_cols; i += blockDim.x) sacc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -625,6 +636,24 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             v[4 * k] += q.x; v[4 * k + 1] += q.y; v[4 * k + 2] += q.z; v[4 * k + 3] += q.w;
           }
         }
+        if ((RE == RE_MASK || RE == RE_BF16) && do_cs) {
+          // column sums over the warp's 32 rows: transpose-reduce butterfly (31 shuffles), lane j ends up
+          // with the sum of column n + j; rows beyond M hold zeros (TMA zero fill) and add nothing
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = (m < p.M) ? v[j] : 0.f;
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int j = 0; j < sft; ++j) {
+              const float send = up ? t[j] : t[j + sft];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, sft);
+              t[j] = (up ? t[j + sft] : t[j]) + recv;
+            }
+          }
+          atomicAdd(sacc + n + lane, t[0]);
+        }
         if (RE == RE_LN) {
           uint32_t w[32];
 #pragma unroll
@@ -740,6 +769,11 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (do_cs)
+    for (int i = threadIdx.x; i < rp.n_cols; i += blockDim.x) {
+      const float vsum = sacc[i];
+      if (vsum != 0.f) atomicAdd(rp.colsum_out + i, vsum);
+    }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -800,7 +834,7 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int MODE_MN>
+template <int BN, int MODE_MN, int CS = 0>
 int launch(const GemmArgs& g, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap mapA, mapB;
@@ -823,7 +857,7 @@ int launch(const GemmArgs& g, cudaStream_t st) {
   const long long tiles = (long long)p.tiles_m * p.tiles_n * p.splits;
   AMC_CHECK_ARG(tiles < (1ll << 30), "gemm_bf16: too many tiles");
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  auto kern = gemm_tc_kernel<BN, MODE_MN>;
+  auto kern = gemm_tc_kernel<BN, MODE_MN, CS>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapB, p, g.epi);
   AMC_LAUNCH_CHECK();
@@ -855,6 +889,10 @@ int launch_row(const GemmArgs& g, cudaStream_t st) {
   rp.bias = e.bias; rp.relu = e.relu; rp.drop = e.drop; rp.drop_site = e.drop_site; rp.mask_scale = e.mask_scale;
   rp.gamma = e.ln_gamma; rp.beta = e.ln_beta; rp.ln_eps = e.ln_eps; rp.rstd = e.ln_rstd;
   rp.has_xhat = e.ln_xhat ? 1 : 0;
+  rp.colsum_out = (C::CS_BYTES > 0 && g.N * 4 <= C::CS_BYTES) ? e.colsum_out : nullptr;
+  rp.n_cols = g.N;
+  AMC_CHECK_ARG(e.colsum_out == nullptr || rp.colsum_out != nullptr,
+                "gemm_bf16: fused column sums need a bf16-output epilogue and N <= 2048");
   const long long tiles = (long long)p.tiles_m * p.tiles_n;
   AMC_CHECK_ARG(tiles < (1ll << 30), "gemm_bf16: too many tiles");
   const int grid = (int)std::min<long long>(tiles, num_sms());
@@ -909,6 +947,12 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
     if (!e.res32 && !e.mask_src && e.D16 && !e.D32) return launch_row_bn<RE_BF16>(best, g, st);
   }
   const int mn = g.transA ? 1 : 0;
+  AMC_CHECK_ARG(e.colsum_out == nullptr || mn, "gemm_bf16: fused column sums are not available for this epilogue");
+  if (mn && e.colsum_out) {
+    if (best == 256) return launch<256, 1, 1>(g, st);
+    if (best == 128) return launch<128, 1, 1>(g, st);
+    return launch<64, 1, 1>(g, st);
+  }
   if (best == 256) return mn ? launch<256, 1>(g, st) : launch<256, 0>(g, st);
   if (best == 128) return mn ? launch<128, 1>(g, st) : launch<128, 0>(g, st);
   return mn ? launch<64, 1>(g, st) : launch<64, 0>(g, st);

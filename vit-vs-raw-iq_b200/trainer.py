@@ -124,11 +124,13 @@ class TrainStep:
 
 
 class HostPipeline:
-    """End-to-end step from HOST buffers: pinned host frames -> (async H2D on a copy stream, double
-    buffered) -> TrainStep.step -> loss read back.  This is the call a user of the reference's loop makes
-    (train.py:254-277: .to(device, non_blocking=True) ... loss.item())."""
+    """End-to-end step from HOST buffers: pinned host frames -> async H2D on a copy stream (double buffered)
+    -> TrainStep.step -> loss read back every step.  This is the loop of train.py:254-277
+    (.to(device, non_blocking=True) ... loss.item()) with one change: ``step`` returns the loss of the
+    PREVIOUS step, so the H2D copy of step i overlaps the compute of step i-1 instead of waiting for it.
+    ``flush()`` returns the last one."""
 
-    def __init__(self, trainer: TrainStep, src_shape, lag: int = 1):
+    def __init__(self, trainer: TrainStep, src_shape):
         self.t = trainer
         dev = trainer.dev
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -136,29 +138,89 @@ class HostPipeline:
                       torch.empty((src_shape[0],), dtype=torch.int64, device=dev)) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
-        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.loss_evt = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.h2d_bytes = self.bufs[0][0].numel() * 4 + self.bufs[0][1].numel() * 8
         self.d2h_bytes = 8
         self.i = 0
+        self.batch = src_shape[0]
 
-    def step(self, src_host: torch.Tensor, labels_host: torch.Tensor) -> float:
+    def step(self, src_host: torch.Tensor, labels_host: torch.Tensor):
         k = self.i & 1
         xs, ys = self.bufs[k]
         cur = torch.cuda.current_stream(self.t.dev)
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.free[k])          # previous user of this buffer is done
+            self.copy_stream.wait_event(self.free[k])          # the step that last used this buffer is done
             xs.copy_(src_host, non_blocking=True)
             ys.copy_(labels_host, non_blocking=True)
             self.ready[k].record(self.copy_stream)
         cur.wait_event(self.ready[k])
         self.t.step(xs, ys)
         self.free[k].record(cur)
-        self.loss_host.copy_(self.t.stats, non_blocking=True)
+        self.loss_host[k].copy_(self.t.stats, non_blocking=True)
         self.t.stats.zero_()
         self.t.frames_seen = 0
+        self.loss_evt[k].record(cur)
+        prev = None
+        if self.i > 0:
+            self.loss_evt[1 - k].synchronize()
+            prev = float(self.loss_host[1 - k][0]) / self.batch
         self.i += 1
-        cur.synchronize()                                      # the reference reads loss.item() every step
-        return float(self.loss_host[0]) / xs.shape[0]
+        return prev
+
+    def flush(self):
+        if self.i == 0:
+            return None
+        k = (self.i - 1) & 1
+        self.loss_evt[k].synchronize()
+        return float(self.loss_host[k][0]) / self.batch
+
+
+class HostPredictor:
+    """Inference from HOST buffers (R/training/utils.py:311-320: images.to(device) -> model(x).max(1) ->
+    predicted.cpu()), double buffered: ``predict`` returns the PREVIOUS batch's class indices (pinned int64
+    tensor, valid until the next-but-one call); ``flush()`` returns the last."""
+
+    def __init__(self, model: _AMCBase, src_shape):
+        self.model = model
+        dev = model.flat_parameters().device
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.x = [torch.empty(src_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.p = [torch.empty((src_shape[0],), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.p_host = [torch.empty((src_shape[0],), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes = self.x[0].numel() * 4
+        self.d2h_bytes = src_shape[0] * 8
+        self.i = 0
+
+    def predict(self, src_host: torch.Tensor):
+        k = self.i & 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])
+            self.x[k].copy_(src_host, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        cur.wait_event(self.ready[k])
+        predict(self.model, self.x[k], self.p[k])
+        self.free[k].record(cur)
+        self.p_host[k].copy_(self.p[k], non_blocking=True)
+        self.done[k].record(cur)
+        prev = None
+        if self.i > 0:
+            self.done[1 - k].synchronize()
+            prev = self.p_host[1 - k]
+        self.i += 1
+        return prev
+
+    def flush(self):
+        if self.i == 0:
+            return None
+        k = (self.i - 1) & 1
+        self.done[k].synchronize()
+        return self.p_host[k]
 
 
 @torch.no_grad()
