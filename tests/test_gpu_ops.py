@@ -95,7 +95,8 @@ def test_gemm_wgrad_split_k(dt, M, N, K):
 @pytest.mark.parametrize("B,T,h,dh", [(3, 9, 8, 32), (2, 65, 8, 16), (2, 129, 4, 8), (1, 257, 8, 32), (5, 17, 4, 48),
                                       (2, 33, 2, 128), (37, 9, 8, 32), (6, 17, 8, 16), (3, 32, 4, 32), (9, 9, 4, 8),
                                       (2, 16, 2, 24), (1, 1, 2, 16), (4, 16, 4, 16), (5, 13, 2, 64), (3, 9, 4, 16),
-                                      (50, 9, 8, 32), (7, 5, 8, 32)])
+                                      (50, 9, 8, 32), (7, 5, 8, 32), (3, 65, 8, 16), (2, 129, 8, 16), (2, 129, 8, 32),
+                                      (2, 100, 4, 64), (4, 33, 8, 32), (1, 288, 2, 16), (3, 48, 4, 32), (2, 257, 16, 16)])
 @pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
 def test_attention_fwd_bwd(dt, B, T, h, dh):
     d = h * dh

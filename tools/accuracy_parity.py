@@ -9,7 +9,7 @@ from vit_vs_raw_iq_b200 import synth
 from vit_vs_raw_iq_b200.trainer import TrainStep, predict
 
 dev = torch.device("cuda:0")
-NTRAIN, NTEST, STEPS, B = 60000, 26000, int(os.environ.get("STEPS", "1500")), 256
+NTRAIN, NTEST, STEPS, B = 60000, 26000, int(os.environ.get("STEPS", "6000")), 256
 t0 = time.time()
 Xtr, ytr, _ = synth.make_frames(NTRAIN, classes=synth.CLASSES_11, seed=42)
 Xte, yte, snr = synth.make_frames(NTEST, classes=synth.CLASSES_11, seed=43)
@@ -30,9 +30,12 @@ def run(seed, dtype, model_kind):
     m._core.seed = 1000 + seed            # same dropout stream for both dtypes
     m.set_raw_input(stats)
     ts = TrainStep(m, lr=1e-3, weight_decay=1e-4)
-    order = np.random.default_rng(seed).permutation(NTRAIN)
+    order = torch.from_numpy(np.random.default_rng(seed).permutation(NTRAIN)).to(dev)
     for it in range(STEPS):
-        idx = torch.from_numpy(order[(it * B) % (NTRAIN - B):][:B]).to(dev)
+        if it and it % max(1, STEPS // 4) == 0:
+            ts.lr *= 0.5                                   # stand-in for ReduceLROnPlateau(factor 0.5)
+        i0 = (it * B) % (NTRAIN - B)
+        idx = order[i0:i0 + B]
         ts.step(xtr[idx].contiguous(), ytr_d[idx].contiguous())
     correct = 0
     for i in range(0, NTEST, 2000):
@@ -42,7 +45,7 @@ def run(seed, dtype, model_kind):
 out = {}
 for kind in ("rawiq", "vit"):
     res = {"fp32": [], "bf16": []}
-    for seed in range(int(os.environ.get("SEEDS", "3"))):
+    for seed in range(int(os.environ.get("SEEDS", "5"))):
         for dt in ("fp32", "bf16"):
             t = time.time()
             acc = run(seed, dt, kind)

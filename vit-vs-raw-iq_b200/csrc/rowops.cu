@@ -163,60 +163,78 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(int M, int d, const flo
     }
   }
   const float inv_d = 1.f / (float)d;
-  for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
-    const size_t base = (size_t)row * d;
-    float dyv[G][8], xh[G][8];
-    float s1 = 0.f, s2 = 0.f;
+  // R rows per warp iteration: all loads are issued before the first reduction so that each warp keeps
+  // R * (48*G) bytes per lane in flight (one row at a time is latency-bound at ~20 rows per warp)
+  constexpr int R = (G == 1) ? 4 : 2;
+  const int wstride = gridDim.x * nw;
+  for (int row0 = (blockIdx.x * nw + warp) * R; row0 < M; row0 += wstride * R) {
+    float dyv[R][G][8], xh[R][G][8];
+    float rs[R];
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      if (on[k]) {
-        const int c0 = k * 256 + lane * 8;
-        const float4 a = *reinterpret_cast<const float4*>(dy + base + c0);
-        const float4 b = *reinterpret_cast<const float4*>(dy + base + c0 + 4);
-        const float4 x0 = load4(xhat + base + c0), x1 = load4(xhat + base + c0 + 4);
-        dyv[k][0] = a.x; dyv[k][1] = a.y; dyv[k][2] = a.z; dyv[k][3] = a.w;
-        dyv[k][4] = b.x; dyv[k][5] = b.y; dyv[k][6] = b.z; dyv[k][7] = b.w;
-        xh[k][0] = x0.x; xh[k][1] = x0.y; xh[k][2] = x0.z; xh[k][3] = x0.w;
-        xh[k][4] = x1.x; xh[k][5] = x1.y; xh[k][6] = x1.z; xh[k][7] = x1.w;
-      } else {
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      const bool rok = row < M;
+      const size_t base = (size_t)(rok ? row : 0) * d;
+      rs[r] = rok ? rstd[row] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { dyv[k][j] = 0.f; xh[k][j] = 0.f; }
-      }
+      for (int k = 0; k < G; ++k) {
+        if (on[k] && rok) {
+          const int c0 = k * 256 + lane * 8;
+          const float4 a = *reinterpret_cast<const float4*>(dy + base + c0);
+          const float4 b = *reinterpret_cast<const float4*>(dy + base + c0 + 4);
+          const float4 x0 = load4(xhat + base + c0), x1 = load4(xhat + base + c0 + 4);
+          dyv[r][k][0] = a.x; dyv[r][k][1] = a.y; dyv[r][k][2] = a.z; dyv[r][k][3] = a.w;
+          dyv[r][k][4] = b.x; dyv[r][k][5] = b.y; dyv[r][k][6] = b.z; dyv[r][k][7] = b.w;
+          xh[r][k][0] = x0.x; xh[r][k][1] = x0.y; xh[r][k][2] = x0.z; xh[r][k][3] = x0.w;
+          xh[r][k][4] = x1.x; xh[r][k][5] = x1.y; xh[r][k][6] = x1.z; xh[r][k][7] = x1.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = dyv[k][j] * g[k][j];
-        s1 += gg;
-        s2 = fmaf(gg, xh[k][j], s2);
-        ag[k][j] = fmaf(dyv[k][j], xh[k][j], ag[k][j]);
-        ab[k][j] += dyv[k][j];
+          for (int j = 0; j < 8; ++j) { dyv[r][k][j] = 0.f; xh[r][k][j] = 0.f; }
+        }
       }
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
-    const float rs = rstd[row];
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      if (!on[k]) continue;
-      const int c0 = k * 256 + lane * 8;
-      float du[8];
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= M) break;
+      const size_t base = (size_t)row * d;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) du[j] = rs * (dyv[k][j] * g[k][j] - s1 - xh[k][j] * s2);
-      if (du32) {
-        *reinterpret_cast<float4*>(du32 + base + c0) = make_float4(du[0], du[1], du[2], du[3]);
-        *reinterpret_cast<float4*>(du32 + base + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
-      }
-      if (drop.p > 0.f) {
-        const float4 m0 = dropout_mult4(drop, site, (uint64_t)(base + c0) >> 2);
-        const float4 m1 = dropout_mult4(drop, site, ((uint64_t)(base + c0) >> 2) + 1);
-        du[0] *= m0.x; du[1] *= m0.y; du[2] *= m0.z; du[3] *= m0.w;
-        du[4] *= m1.x; du[5] *= m1.y; du[6] *= m1.z; du[7] *= m1.w;
-      }
-      if (du16) {
-        store4(du16 + base + c0, make_float4(du[0], du[1], du[2], du[3]));
-        store4(du16 + base + c0 + 4, make_float4(du[4], du[5], du[6], du[7]));
-      }
+      for (int k = 0; k < G; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ad[k][j] += du[j];
+        for (int j = 0; j < 8; ++j) {
+          const float gg = dyv[r][k][j] * g[k][j];
+          s1 += gg;
+          s2 = fmaf(gg, xh[r][k][j], s2);
+          ag[k][j] = fmaf(dyv[r][k][j], xh[r][k][j], ag[k][j]);
+          ab[k][j] += dyv[r][k][j];
+        }
+      s1 = warp_sum(s1) * inv_d;
+      s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        if (!on[k]) continue;
+        const int c0 = k * 256 + lane * 8;
+        float du[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) du[j] = rs[r] * (dyv[r][k][j] * g[k][j] - s1 - xh[r][k][j] * s2);
+        if (du32) {
+          *reinterpret_cast<float4*>(du32 + base + c0) = make_float4(du[0], du[1], du[2], du[3]);
+          *reinterpret_cast<float4*>(du32 + base + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
+        }
+        if (drop.p > 0.f) {
+          const float4 m0 = dropout_mult4(drop, site, (uint64_t)(base + c0) >> 2);
+          const float4 m1 = dropout_mult4(drop, site, ((uint64_t)(base + c0) >> 2) + 1);
+          du[0] *= m0.x; du[1] *= m0.y; du[2] *= m0.z; du[3] *= m0.w;
+          du[4] *= m1.x; du[5] *= m1.y; du[6] *= m1.z; du[7] *= m1.w;
+        }
+        if (du16) {
+          store4(du16 + base + c0, make_float4(du[0], du[1], du[2], du[3]));
+          store4(du16 + base + c0 + 4, make_float4(du[4], du[5], du[6], du[7]));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad[k][j] += du[j];
+      }
     }
   }
   // block reduction (8 warps) then one atomic per column per block
