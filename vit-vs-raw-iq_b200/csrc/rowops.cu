@@ -137,125 +137,103 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(int M, int d, const float* 
   }
 }
 
-// Vectorised LayerNorm backward for d % 8 == 0: each lane owns 8 consecutive columns per 256-column
-// group (32-byte fp32 / 16-byte bf16 accesses, a whole row is one contiguous warp transaction).  Besides
-// dgamma/dbeta it also accumulates the column sums of the (dropout-masked) du16 it writes, i.e. the bias
-// gradient of the sub-layer's output projection (Appendix B: db = sum d_out), saving a pass over du16.
-template <typename E, int G>   // G = number of 256-column groups (d <= 256*G)
+// Vectorised LayerNorm backward for d = 128 * NV (NV = 1..4): each lane owns 4*NV consecutive columns, so a
+// row is one contiguous, fully coalesced warp transaction (16*NV B fp32 / 8*NV B bf16 per lane) and every
+// lane is busy.  Besides dgamma/dbeta it also accumulates the column sums of the (dropout-masked) du16 it
+// writes, i.e. the bias gradient of the sub-layer's output projection (Appendix B: db = sum d_out), saving
+// a pass over du16.  R rows per warp iteration keep enough loads in flight.
+template <typename E, int NV>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(int M, int d, const float* __restrict__ dy,
                                                          const E* __restrict__ xhat, const float* __restrict__ rstd,
                                                          const float* __restrict__ gamma, E* __restrict__ du16,
                                                          float* __restrict__ du32, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta, float* __restrict__ dbias,
                                                          DropoutCfg drop, uint32_t site) {
-  __shared__ float red[3][8][G * 256 / 8 + 1];   // [acc][warp][column slot] -- reduced 8 columns at a time below
+  constexpr int CPL = 4 * NV;                     // columns per lane
+  constexpr int R = (NV <= 2) ? 4 : 2;
+  __shared__ float red[3][8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float g[G][8], ag[G][8], ab[G][8], ad[G][8];
-  bool on[G];
+  const int c0 = lane * CPL;
+  float g[CPL], ag[CPL], ab[CPL], ad[CPL];
 #pragma unroll
-  for (int k = 0; k < G; ++k) {
-    const int c0 = k * 256 + lane * 8;
-    on[k] = c0 < d;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      g[k][j] = on[k] ? __ldg(gamma + c0 + j) : 0.f;
-      ag[k][j] = 0.f; ab[k][j] = 0.f; ad[k][j] = 0.f;
-    }
+  for (int j = 0; j < CPL; ++j) {
+    g[j] = __ldg(gamma + c0 + j);
+    ag[j] = 0.f; ab[j] = 0.f; ad[j] = 0.f;
   }
   const float inv_d = 1.f / (float)d;
-  // R rows per warp iteration: all loads are issued before the first reduction so that each warp keeps
-  // R * (48*G) bytes per lane in flight (one row at a time is latency-bound at ~20 rows per warp)
-  constexpr int R = (G == 1) ? 4 : 2;
   const int wstride = gridDim.x * nw;
   for (int row0 = (blockIdx.x * nw + warp) * R; row0 < M; row0 += wstride * R) {
-    float dyv[R][G][8], xh[R][G][8];
-    float rs[R];
+    float dyv[R][CPL], xh[R][CPL], rs[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = row0 + r;
       const bool rok = row < M;
-      const size_t base = (size_t)(rok ? row : 0) * d;
+      const size_t base = (size_t)(rok ? row : 0) * d + c0;
       rs[r] = rok ? rstd[row] : 0.f;
 #pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (on[k] && rok) {
-          const int c0 = k * 256 + lane * 8;
-          const float4 a = *reinterpret_cast<const float4*>(dy + base + c0);
-          const float4 b = *reinterpret_cast<const float4*>(dy + base + c0 + 4);
-          const float4 x0 = load4(xhat + base + c0), x1 = load4(xhat + base + c0 + 4);
-          dyv[r][k][0] = a.x; dyv[r][k][1] = a.y; dyv[r][k][2] = a.z; dyv[r][k][3] = a.w;
-          dyv[r][k][4] = b.x; dyv[r][k][5] = b.y; dyv[r][k][6] = b.z; dyv[r][k][7] = b.w;
-          xh[r][k][0] = x0.x; xh[r][k][1] = x0.y; xh[r][k][2] = x0.z; xh[r][k][3] = x0.w;
-          xh[r][k][4] = x1.x; xh[r][k][5] = x1.y; xh[r][k][6] = x1.z; xh[r][k][7] = x1.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { dyv[r][k][j] = 0.f; xh[r][k][j] = 0.f; }
+      for (int v = 0; v < NV; ++v) {
+        float4 a = make_float4(0, 0, 0, 0), x = make_float4(0, 0, 0, 0);
+        if (rok) {
+          a = *reinterpret_cast<const float4*>(dy + base + 4 * v);
+          x = load4(xhat + base + 4 * v);
         }
+        dyv[r][4 * v] = a.x; dyv[r][4 * v + 1] = a.y; dyv[r][4 * v + 2] = a.z; dyv[r][4 * v + 3] = a.w;
+        xh[r][4 * v] = x.x; xh[r][4 * v + 1] = x.y; xh[r][4 * v + 2] = x.z; xh[r][4 * v + 3] = x.w;
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = row0 + r;
       if (row >= M) break;
-      const size_t base = (size_t)row * d;
+      const size_t base = (size_t)row * d + c0;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < G; ++k)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = dyv[r][k][j] * g[k][j];
-          s1 += gg;
-          s2 = fmaf(gg, xh[r][k][j], s2);
-          ag[k][j] = fmaf(dyv[r][k][j], xh[r][k][j], ag[k][j]);
-          ab[k][j] += dyv[r][k][j];
-        }
+      for (int j = 0; j < CPL; ++j) {
+        const float gg = dyv[r][j] * g[j];
+        s1 += gg;
+        s2 = fmaf(gg, xh[r][j], s2);
+        ag[j] = fmaf(dyv[r][j], xh[r][j], ag[j]);
+        ab[j] += dyv[r][j];
+      }
       s1 = warp_sum(s1) * inv_d;
       s2 = warp_sum(s2) * inv_d;
+      float du[CPL];
 #pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (!on[k]) continue;
-        const int c0 = k * 256 + lane * 8;
-        float du[8];
+      for (int j = 0; j < CPL; ++j) du[j] = rs[r] * (dyv[r][j] * g[j] - s1 - xh[r][j] * s2);
+      if (du32) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) du[j] = rs[r] * (dyv[r][k][j] * g[k][j] - s1 - xh[r][k][j] * s2);
-        if (du32) {
-          *reinterpret_cast<float4*>(du32 + base + c0) = make_float4(du[0], du[1], du[2], du[3]);
-          *reinterpret_cast<float4*>(du32 + base + c0 + 4) = make_float4(du[4], du[5], du[6], du[7]);
-        }
-        if (drop.p > 0.f) {
-          const float4 m0 = dropout_mult4(drop, site, (uint64_t)(base + c0) >> 2);
-          const float4 m1 = dropout_mult4(drop, site, ((uint64_t)(base + c0) >> 2) + 1);
-          du[0] *= m0.x; du[1] *= m0.y; du[2] *= m0.z; du[3] *= m0.w;
-          du[4] *= m1.x; du[5] *= m1.y; du[6] *= m1.z; du[7] *= m1.w;
-        }
-        if (du16) {
-          store4(du16 + base + c0, make_float4(du[0], du[1], du[2], du[3]));
-          store4(du16 + base + c0 + 4, make_float4(du[4], du[5], du[6], du[7]));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ad[k][j] += du[j];
+        for (int v = 0; v < NV; ++v)
+          *reinterpret_cast<float4*>(du32 + base + 4 * v) = make_float4(du[4 * v], du[4 * v + 1], du[4 * v + 2], du[4 * v + 3]);
       }
+      if (drop.p > 0.f) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 mk = dropout_mult4(drop, site, ((uint64_t)base >> 2) + v);
+          du[4 * v] *= mk.x; du[4 * v + 1] *= mk.y; du[4 * v + 2] *= mk.z; du[4 * v + 3] *= mk.w;
+        }
+      }
+      if (du16) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          store4(du16 + base + 4 * v, make_float4(du[4 * v], du[4 * v + 1], du[4 * v + 2], du[4 * v + 3]));
+      }
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) ad[j] += du[j];
     }
   }
   // block reduction (8 warps) then one atomic per column per block
 #pragma unroll
-  for (int k = 0; k < G; ++k) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __syncthreads();
-      red[0][warp][lane] = ag[k][j];
-      red[1][warp][lane] = ab[k][j];
-      red[2][warp][lane] = ad[k][j];
-      __syncthreads();
-      if (warp < 3) {
-        float t = 0.f;
-        for (int w = 0; w < nw; ++w) t += red[warp][w][lane];
-        const int c = k * 256 + lane * 8 + j;
-        if (c < d) {
-          float* dst = warp == 0 ? dgamma : (warp == 1 ? dbeta : dbias);
-          if (dst) atomicAdd(dst + c, t);
-        }
-      }
+  for (int j = 0; j < CPL; ++j) {
+    __syncthreads();
+    red[0][warp][lane] = ag[j];
+    red[1][warp][lane] = ab[j];
+    red[2][warp][lane] = ad[j];
+    __syncthreads();
+    if (warp < 3) {
+      float t = 0.f;
+      for (int w = 0; w < nw; ++w) t += red[warp][w][lane];
+      float* dst = warp == 0 ? dgamma : (warp == 1 ? dbeta : dbias);
+      if (dst) atomicAdd(dst + c0 + j, t);
     }
   }
 }
@@ -704,14 +682,17 @@ int ln_bwd(int M, int d, const float* dy, const E* xhat, const float* rstd, cons
   AMC_CHECK_ARG(d >= 1 && d <= 32 * MAXV, "layernorm_bwd: d=%d unsupported (1..512)", d);
   if (M == 0) return 0;
   auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
-  if (d % 8 == 0 && al(dy, 16) && al(xhat, 16) && al(du16, 16) && al(du32, 16)) {
-    const int blocks = std::min(ceil_div(M, 8), 148 * 3);
-    if (d <= 256)
-      ln_bwd_vec_kernel<E, 1><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, dbias,
-                                                      drop, site);
-    else
-      ln_bwd_vec_kernel<E, 2><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, dbias,
-                                                      drop, site);
+  if (d % 128 == 0 && al(dy, 16) && al(xhat, 16) && al(du16, 16) && al(du32, 16) && al(gamma, 4)) {
+    const int nv = d / 128;
+    const int blocks = std::min(ceil_div(M, 8 * (nv <= 2 ? 4 : 2)), 148 * 2);
+#define AMC_LN_BWD(NV)                                                                                           \
+  ln_bwd_vec_kernel<E, NV><<<blocks, 256, 0, st>>>(M, d, dy, xhat, rstd, gamma, du16, du32, dgamma, dbeta, dbias, \
+                                                   drop, site)
+    if (nv == 1) AMC_LN_BWD(1);
+    else if (nv == 2) AMC_LN_BWD(2);
+    else if (nv == 3) AMC_LN_BWD(3);
+    else AMC_LN_BWD(4);
+#undef AMC_LN_BWD
     AMC_LAUNCH_CHECK();
     return 0;
   }
