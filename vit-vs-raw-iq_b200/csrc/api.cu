@@ -33,6 +33,14 @@ __global__ void add_inplace_kernel(size_t n, float* __restrict__ a, const float*
     a[i] += b[i];
 }
 
+// dst[b * ld + c] += src[b * d + c]
+__global__ void add_rows_kernel(int B, int d, float* __restrict__ dst, int ld, const float* __restrict__ src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int b = i / d, c = i - b * d;
+  dst[(size_t)b * ld + c] += src[i];
+}
+
 struct Dims {
   int B, T, Ttok, K, d, h, dh, F, C, L, has_cls;
   int64_t M;  // B*T token rows
@@ -124,6 +132,11 @@ struct Work {
   std::vector<float*> x32;
   std::vector<LayerBuf> lay;  // L (training) or 1
   float *u32, *hl, *hxhat, *hrstd, *dhl;
+  // compact [B, .] buffers of the top layer when only its CLS rows are live (see Model::cls_top)
+  struct Cls {
+    void *x1_16, *hid, *xhat1, *xhat2, *y16, *dw16, *da, *du16;
+    float *x1_32, *rstd1, *rstd2, *y32, *u32, *dy32, *dw32, *t32, *du32;
+  } c;
   // backward scratch
   float *dy32, *dw32, *t32, *du32;
   void *dw16, *da, *du16, *dO, *dqkv, *demb;
@@ -179,6 +192,28 @@ void carve(const AmcDesc& D, const Dims& m, const AmcParamLayout& L, char* base,
   w.hxhat = (float*)take((size_t)m.B * d * 4);
   w.hrstd = (float*)take((size_t)m.B * 4);
   w.dhl = (float*)take((size_t)m.B * d * 4);
+  {
+    const size_t Bq = (size_t)m.B;
+    w.c.x1_16 = take(Bq * d * e);
+    w.c.x1_32 = bf ? (float*)take(Bq * d * 4) : (float*)w.c.x1_16;
+    w.c.hid = take(Bq * F * e);
+    w.c.y16 = take(Bq * d * e);
+    w.c.y32 = bf ? (float*)take(Bq * d * 4) : (float*)w.c.y16;
+    w.c.u32 = (float*)take(Bq * d * 4);
+    w.c.xhat1 = D.training ? take(Bq * d * e) : nullptr;
+    w.c.xhat2 = D.training ? take(Bq * d * e) : nullptr;
+    w.c.rstd1 = D.training ? (float*)take(Bq * 4) : nullptr;
+    w.c.rstd2 = D.training ? (float*)take(Bq * 4) : nullptr;
+    if (D.training) {
+      w.c.dy32 = (float*)take(Bq * d * 4);
+      w.c.dw32 = (float*)take(Bq * d * 4);
+      w.c.t32 = (float*)take(Bq * d * 4);
+      w.c.du32 = (float*)take(Bq * d * 4);
+      w.c.dw16 = take(Bq * d * e);
+      w.c.da = take(Bq * F * e);
+      w.c.du16 = take(Bq * d * e);
+    }
+  }
   if (D.training) {
     w.dy32 = (float*)take(M * d * 4);
     w.dw32 = (float*)take(M * d * 4);
@@ -299,77 +334,129 @@ struct Model {
     return 0;
   }
 
-  int layer_fwd(int l) {
-    const int M = (int)m.M, d = m.d, F = m.F;
+  // The rows a layer's post-attention half (out-proj, norm1, FFN, norm2) works on.  Normally all M = B*T token
+  // rows; for the top layer of a CLS-pooled model only the B CLS rows feed the head, so that half runs on a
+  // B-row view (attention output and residual read with row pitch T*d, everything else compact).
+  struct Rows {
+    int n;                                  // rows
+    const void* o; int ldo;                 // attention output rows
+    const float* xres; int ldxres;          // fp32 residual of the layer input
+    const void* xin16; int ldxin;           // layer input rows (weight gradient of nothing here; kept for clarity)
+    void *x1_16, *hid, *xhat1, *xhat2, *y16;
+    float *x1_32, *rstd1, *rstd2, *y32, *u32;
+    // backward
+    float *dy32, *dw32, *t32, *du32;
+    void *dw16, *da, *du16;
+    void* dO; int lddO;                     // where the out-proj input gradient goes (row pitch)
+  };
+  Rows all_rows(int l) {
     const LayerBuf& b = LB(l);
-    const int xin = xi(l), xout = xi(l + 1);
+    Rows r;
+    r.n = (int)m.M; r.o = b.o; r.ldo = m.d; r.xres = w.x32[xi(l)]; r.ldxres = m.d;
+    r.xin16 = w.x16[xi(l)]; r.ldxin = m.d;
+    r.x1_16 = b.x1_16; r.hid = b.hid; r.xhat1 = b.xhat1; r.xhat2 = b.xhat2; r.y16 = w.x16[xi(l + 1)];
+    r.x1_32 = b.x1_32; r.rstd1 = b.rstd1; r.rstd2 = b.rstd2; r.y32 = w.x32[xi(l + 1)]; r.u32 = w.u32;
+    r.dy32 = w.dy32; r.dw32 = w.dw32; r.t32 = w.t32; r.du32 = w.du32;
+    r.dw16 = w.dw16; r.da = w.da; r.du16 = w.du16; r.dO = w.dO; r.lddO = m.d;
+    return r;
+  }
+  Rows cls_rows_view(int l) {
+    const LayerBuf& b = LB(l);
+    const int Td = m.T * m.d;
+    Rows r;
+    r.n = m.B; r.o = b.o; r.ldo = Td; r.xres = w.x32[xi(l)]; r.ldxres = Td;
+    r.xin16 = w.x16[xi(l)]; r.ldxin = Td;
+    r.x1_16 = w.c.x1_16; r.hid = w.c.hid; r.xhat1 = w.c.xhat1; r.xhat2 = w.c.xhat2; r.y16 = w.c.y16;
+    r.x1_32 = w.c.x1_32; r.rstd1 = w.c.rstd1; r.rstd2 = w.c.rstd2; r.y32 = w.c.y32; r.u32 = w.c.u32;
+    r.dy32 = w.c.dy32; r.dw32 = w.c.dw32; r.t32 = w.c.t32; r.du32 = w.c.du32;
+    r.dw16 = w.c.dw16; r.da = w.c.da; r.du16 = w.c.du16; r.dO = w.dO; r.lddO = Td;
+    return r;
+  }
+
+  // fused QKV projection (one [3d,d] weight: three adjacent state_dict tensors, multi_head_attention.py:18)
+  // + attention over all rows
+  int attn_fwd_part(int l) {
+    const int M = (int)m.M, d = m.d;
+    const LayerBuf& b = LB(l);
     GemmArgs g;
-    // fused QKV projection: one [3d,d] weight (three state_dict tensors, adjacent) -- multi_head_attention.py:18
-    g = GemmArgs();
-    g.M = M; g.N = 3 * d; g.K = d; g.A = w.x16[xin]; g.lda = d; g.B = WL(l, L.wq); g.ldb = d;
+    g.M = M; g.N = 3 * d; g.K = d; g.A = w.x16[xi(l)]; g.lda = d; g.B = WL(l, L.wq); g.ldb = d;
     g.name = "gemm_qkv";
     g.epi.bias = PL(l, L.bq); g.epi.D16 = b.qkv; g.epi.ldd16 = 3 * d;
     AMC_TRY(gemm<E>(g, st));
-    {
-      ProfScope ps("attn_fwd", st, 4.0 * m.M * m.T * d, (double)M * 4 * d * sizeof(E));
-      AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
-    }
+    ProfScope ps("attn_fwd", st, 4.0 * m.M * m.T * d, (double)M * 4 * d * sizeof(E));
+    AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
+    return 0;
+  }
+
+  int post_fwd_part(int l, const Rows& r) {
+    const int d = m.d, F = m.F, Mr = r.n;
+    GemmArgs g;
     // out-proj + dropout1 + residual -> u ; norm1 (encoder_layer.py:24-25)
-    g = GemmArgs();
-    g.M = M; g.N = d; g.K = d; g.A = b.o; g.lda = d; g.B = WL(l, L.wo); g.ldb = d;
+    g.M = Mr; g.N = d; g.K = d; g.A = r.o; g.lda = r.ldo; g.B = WL(l, L.wo); g.ldb = d;
     g.name = "gemm_outproj";
     g.epi.bias = PL(l, L.bo); g.epi.drop = drop; g.epi.drop_site = site_attn(l);
-    g.epi.res32 = w.x32[xin]; g.epi.ldres = d;
+    g.epi.res32 = r.xres; g.epi.ldres = r.ldxres;
     if (fuse_ln()) {   // bias + dropout + residual + LayerNorm inside the GEMM epilogue (row-owned in TMEM)
       g.name = "gemm_outproj_ln";
       g.epi.ln_gamma = PL(l, L.g1); g.epi.ln_beta = PL(l, L.be1); g.epi.ln_eps = D.ln_eps;
-      g.epi.D16 = b.x1_16; g.epi.ldd16 = d; g.epi.D32 = b.x1_32; g.epi.ldd32 = d;
-      g.epi.ln_xhat = b.xhat1; g.epi.ln_rstd = b.rstd1;
+      g.epi.D16 = r.x1_16; g.epi.ldd16 = d; g.epi.D32 = r.x1_32; g.epi.ldd32 = d;
+      g.epi.ln_xhat = r.xhat1; g.epi.ln_rstd = r.rstd1;
       AMC_TRY(gemm<E>(g, st));
     } else {
-      g.epi.D32 = w.u32; g.epi.ldd32 = d;
+      g.epi.D32 = r.u32; g.epi.ldd32 = d;
       AMC_TRY(gemm<E>(g, st));
-      AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)b.x1_16,
-                        sizeof(E) == 2 ? b.x1_32 : nullptr, (E*)b.xhat1, b.rstd1, st));
+      AMC_PROF("ln_fwd", 0.0, (double)Mr * d * (8 + 2 * sizeof(E)),
+               ln_fwd<E>(Mr, d, r.u32, PL(l, L.g1), PL(l, L.be1), D.ln_eps, (E*)r.x1_16,
+                         sizeof(E) == 2 ? r.x1_32 : nullptr, (E*)r.xhat1, r.rstd1, st));
     }
     // FFN (position_wise_feed_forward.py:12-17): linear1 + ReLU + dropout
     g = GemmArgs();
-    g.M = M; g.N = F; g.K = d; g.A = b.x1_16; g.lda = d; g.B = WL(l, L.w1); g.ldb = d;
+    g.M = Mr; g.N = F; g.K = d; g.A = r.x1_16; g.lda = d; g.B = WL(l, L.w1); g.ldb = d;
     g.name = "gemm_ffn1";
     g.epi.bias = PL(l, L.b1); g.epi.relu = 1; g.epi.drop = drop; g.epi.drop_site = site_hidden(l);
-    g.epi.D16 = b.hid; g.epi.ldd16 = F;
+    g.epi.D16 = r.hid; g.epi.ldd16 = F;
     AMC_TRY(gemm<E>(g, st));
     // linear2 + dropout2 + residual -> u ; norm2 (encoder_layer.py:32-33)
     g = GemmArgs();
-    g.M = M; g.N = d; g.K = F; g.A = b.hid; g.lda = F; g.B = WL(l, L.w2); g.ldb = F;
+    g.M = Mr; g.N = d; g.K = F; g.A = r.hid; g.lda = F; g.B = WL(l, L.w2); g.ldb = F;
     g.name = "gemm_ffn2";
     g.epi.bias = PL(l, L.b2); g.epi.drop = drop; g.epi.drop_site = site_ffn(l);
-    g.epi.res32 = b.x1_32; g.epi.ldres = d;
+    g.epi.res32 = r.x1_32; g.epi.ldres = d;
     if (fuse_ln()) {
       g.name = "gemm_ffn2_ln";
       g.epi.ln_gamma = PL(l, L.g2); g.epi.ln_beta = PL(l, L.be2); g.epi.ln_eps = D.ln_eps;
-      g.epi.D16 = w.x16[xout]; g.epi.ldd16 = d; g.epi.D32 = w.x32[xout]; g.epi.ldd32 = d;
-      g.epi.ln_xhat = b.xhat2; g.epi.ln_rstd = b.rstd2;
+      g.epi.D16 = r.y16; g.epi.ldd16 = d; g.epi.D32 = r.y32; g.epi.ldd32 = d;
+      g.epi.ln_xhat = r.xhat2; g.epi.ln_rstd = r.rstd2;
       AMC_TRY(gemm<E>(g, st));
     } else {
-      g.epi.D32 = w.u32; g.epi.ldd32 = d;
+      g.epi.D32 = r.u32; g.epi.ldd32 = d;
       AMC_TRY(gemm<E>(g, st));
-      AMC_PROF("ln_fwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_fwd<E>(M, d, w.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)w.x16[xout],
-                        sizeof(E) == 2 ? w.x32[xout] : nullptr, (E*)b.xhat2, b.rstd2, st));
+      AMC_PROF("ln_fwd", 0.0, (double)Mr * d * (8 + 2 * sizeof(E)),
+               ln_fwd<E>(Mr, d, r.u32, PL(l, L.g2), PL(l, L.be2), D.ln_eps, (E*)r.y16,
+                         sizeof(E) == 2 ? r.y32 : nullptr, (E*)r.xhat2, r.rstd2, st));
     }
     return 0;
+  }
+
+  int layer_fwd(int l, bool cls_only) {
+    AMC_TRY(attn_fwd_part(l));
+    return post_fwd_part(l, cls_only ? cls_rows_view(l) : all_rows(l));
   }
 
   int forward(const float* src, const float* pos, float* logits, float* enc_out) {
     if (m.B == 0) return 0;
     AMC_TRY(pack_weights());
     AMC_TRY(frontend(src, pos));
-    for (int l = 0; l < m.L; ++l) AMC_TRY(layer_fwd(l));
-    const float* xL = w.x32[xi(m.L)];
+    // Only the CLS rows of the top layer reach the head (transformer_rawIQ.py:88-90, amc_transformer.py:29): when
+    // just the logits are wanted, the top layer's out-proj / FFN / LayerNorms run on those B rows alone.
+    const bool cls_top = m.has_cls && logits && !enc_out && m.L >= 1;
+    for (int l = 0; l < m.L; ++l) AMC_TRY(layer_fwd(l, cls_top && l == m.L - 1));
+    const float* xL = cls_top ? w.c.y32 : w.x32[xi(m.L)];
+    const int headT = cls_top ? 1 : m.T;
     if (enc_out)
       AMC_CUDA(cudaMemcpyAsync(enc_out, xL, (size_t)m.M * m.d * 4, cudaMemcpyDeviceToDevice, st));
     if (logits)
-      AMC_PROF("head", 0.0, 0.0, head_fwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, D.head_ln_eps, xL,
+      AMC_PROF("head", 0.0, 0.0, head_fwd(m.B, headT, m.d, m.C, m.has_cls, D.head_ln, D.head_ln_eps, xL,
                        D.head_ln ? P(L.head_ln_w) : nullptr, D.head_ln ? P(L.head_ln_b) : nullptr, P(L.head_w),
                        P(L.head_b), logits, w.hl, w.hxhat, w.hrstd, st));
     return 0;
@@ -401,56 +488,91 @@ struct Model {
     }
   }
 
-  int layer_bwd(int l, float* grads) {
-    const int M = (int)m.M, d = m.d, F = m.F;
+  // wgrad with an explicit token count (the CLS view has B token rows)
+  int wgrad_n(int Ktok, int No, int Ki, const void* dY, int ldy, const void* X, int ldx, float* dW, float* db) {
+    if (db && sizeof(E) != 2) AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Ktok, No, (const E*)dY, ldy, db, st));
+    GemmArgs g;
+    if (sizeof(E) == 2) g.epi.colsum_out = db;
+    g.M = No; g.N = Ki; g.K = Ktok;
+    g.A = dY; g.lda = ldy; g.transA = 1;
+    g.B = X; g.ldb = ldx; g.transB = 1;
+    g.split_k = pick_split_k(No, Ki, g.K);
+    g.name = "gemm_wgrad";
+    g.epi.D32 = dW; g.epi.ldd32 = Ki; g.epi.accumulate = 1;
+    return gemm<E>(g, st);
+  }
+
+  // backward of post_fwd_part on the same row view: consumes r.dy32, leaves the out-proj input gradient in
+  // r.dO (row pitch r.lddO) and the skip gradient of the layer input in r.du32
+  int post_bwd_part(int l, const Rows& r, float* grads) {
+    const int d = m.d, F = m.F, Mr = r.n;
     const int64_t dd = (int64_t)d * d;
-    const LayerBuf& b = LB(l);
     float* G = grads + L.layer0 + (int64_t)l * L.layer_stride;
     GemmArgs g;
     // norm2 backward; dw16 carries dropout2's mask (operand of the FFN2 gradients), dw32 is the skip path
-    AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.dy32, (const E*)b.xhat2, b.rstd2, PL(l, L.g2), (E*)w.dw16, w.dw32, G + L.g2,
-                      G + L.be2, G + L.b2, drop, site_ffn(l), st));
-    AMC_TRY(wgrad(d, F, w.dw16, d, b.hid, F, G + L.w2, nullptr));
+    AMC_PROF("ln_bwd", 0.0, (double)Mr * d * (8 + 2 * sizeof(E)),
+             ln_bwd<E>(Mr, d, r.dy32, (const E*)r.xhat2, r.rstd2, PL(l, L.g2), (E*)r.dw16, r.dw32, G + L.g2, G + L.be2,
+                       G + L.b2, drop, site_ffn(l), st));
+    AMC_TRY(wgrad_n(Mr, d, F, r.dw16, d, r.hid, F, G + L.w2, nullptr));
     // dgrad FFN2 with the ReLU/dropout mask taken from the stored hidden
-    g = GemmArgs();
-    g.M = M; g.N = F; g.K = d; g.A = w.dw16; g.lda = d;
+    g.M = Mr; g.N = F; g.K = d; g.A = r.dw16; g.lda = d;
     dgrad_operand(g, l, L.w2, 4 * dd + (int64_t)d * F, d, F);
     g.name = "gemm_dgrad_ffn2";
-    g.epi.mask_src = b.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
-    g.epi.D16 = w.da; g.epi.ldd16 = F;
+    g.epi.mask_src = r.hid; g.epi.ldmask = F; g.epi.mask_scale = drop.scale;
+    g.epi.D16 = r.da; g.epi.ldd16 = F;
     const bool fuse_db1 = sizeof(E) == 2 && F % 32 == 0 && F <= 2048;   // bias gradient summed in the mask epilogue
     if (fuse_db1) g.epi.colsum_out = G + L.b1;
     AMC_TRY(gemm<E>(g, st));
-    AMC_TRY(wgrad(F, d, w.da, F, b.x1_16, d, G + L.w1, fuse_db1 ? nullptr : G + L.b1));
+    AMC_TRY(wgrad_n(Mr, F, d, r.da, F, r.x1_16, d, G + L.w1, fuse_db1 ? nullptr : G + L.b1));
     // dgrad FFN1 + skip -> gradient w.r.t. x1
     g = GemmArgs();
-    g.M = M; g.N = d; g.K = F; g.A = w.da; g.lda = F;
+    g.M = Mr; g.N = d; g.K = F; g.A = r.da; g.lda = F;
     dgrad_operand(g, l, L.w1, 4 * dd, F, d);
     g.name = "gemm_dgrad_ffn1";
-    g.epi.res32 = w.dw32; g.epi.ldres = d; g.epi.D32 = w.t32; g.epi.ldd32 = d;
+    g.epi.res32 = r.dw32; g.epi.ldres = d; g.epi.D32 = r.t32; g.epi.ldd32 = d;
     AMC_TRY(gemm<E>(g, st));
     // norm1 backward
-    AMC_PROF("ln_bwd", 0.0, (double)m.M * m.d * (8 + 2 * sizeof(E)), ln_bwd<E>(M, d, w.t32, (const E*)b.xhat1, b.rstd1, PL(l, L.g1), (E*)w.du16, w.du32, G + L.g1,
-                      G + L.be1, G + L.bo, drop, site_attn(l), st));
-    AMC_TRY(wgrad(d, d, w.du16, d, b.o, d, G + L.wo, nullptr));
+    AMC_PROF("ln_bwd", 0.0, (double)Mr * d * (8 + 2 * sizeof(E)),
+             ln_bwd<E>(Mr, d, r.t32, (const E*)r.xhat1, r.rstd1, PL(l, L.g1), (E*)r.du16, r.du32, G + L.g1, G + L.be1,
+                       G + L.bo, drop, site_attn(l), st));
+    AMC_TRY(wgrad_n(Mr, d, d, r.du16, d, r.o, r.ldo, G + L.wo, nullptr));
     g = GemmArgs();
-    g.M = M; g.N = d; g.K = d; g.A = w.du16; g.lda = d;
+    g.M = Mr; g.N = d; g.K = d; g.A = r.du16; g.lda = d;
     dgrad_operand(g, l, L.wo, 3 * dd, d, d);
     g.name = "gemm_dgrad_outproj";
-    g.epi.D16 = w.dO; g.epi.ldd16 = d;
+    g.epi.D16 = r.dO; g.epi.ldd16 = r.lddO;
     AMC_TRY(gemm<E>(g, st));
+    return 0;
+  }
+
+  int layer_bwd(int l, float* grads, bool cls_only) {
+    const int M = (int)m.M, d = m.d;
+    const LayerBuf& b = LB(l);
+    float* G = grads + L.layer0 + (int64_t)l * L.layer_stride;
+    if (cls_only) {
+      // every non-CLS row of the attention-output gradient is exactly zero
+      AMC_CUDA(cudaMemsetAsync(w.dO, 0, (size_t)M * d * sizeof(E), st));
+      AMC_TRY(post_bwd_part(l, cls_rows_view(l), grads));
+    } else {
+      AMC_TRY(post_bwd_part(l, all_rows(l), grads));
+    }
     {
       ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
       AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, G + L.bq, st));
     }
     AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq, nullptr));
     // dgrad QKV + skip -> gradient w.r.t. the layer input
-    g = GemmArgs();
+    GemmArgs g;
     g.M = M; g.N = d; g.K = 3 * d; g.A = w.dqkv; g.lda = 3 * d;
     dgrad_operand(g, l, L.wq, 0, 3 * d, d);
     g.name = "gemm_dgrad_qkv";
-    g.epi.res32 = w.du32; g.epi.ldres = d; g.epi.D32 = w.dy32; g.epi.ldd32 = d;
+    g.epi.D32 = w.dy32; g.epi.ldd32 = d;
+    if (!cls_only) { g.epi.res32 = w.du32; g.epi.ldres = d; }
     AMC_TRY(gemm<E>(g, st));
+    if (cls_only) {   // the skip gradient exists on the CLS rows only
+      add_rows_kernel<<<ceil_div(m.B * d, 256), 256, 0, st>>>(m.B, d, w.dy32, m.T * d, w.c.du32);
+      AMC_LAUNCH_CHECK();
+    }
     return 0;
   }
 
@@ -459,12 +581,14 @@ struct Model {
     AMC_CHECK_ARG(0 <= s0 && s0 <= s1 && s1 <= m.L + 2, "bad stage range [%d,%d)", s0, s1);
     if (m.B == 0) return 0;
     const size_t nx = (size_t)m.M * m.d;
+    const bool cls_top = m.has_cls && dlogits && !denc_out && m.L >= 1;   // must mirror forward()
     for (int s = s0; s < s1; ++s) {
       if (s == 0) {
         AMC_CHECK_ARG(dlogits || denc_out, "amc_model_bwd: dlogits and denc_out are both NULL");
         if (dlogits) {
-          AMC_PROF("head", 0.0, 0.0, head_bwd(m.B, m.T, m.d, m.C, m.has_cls, D.head_ln, dlogits, P(L.head_w),
-                           D.head_ln ? P(L.head_ln_w) : nullptr, w.hl, w.hxhat, w.hrstd, w.dhl, w.dy32,
+          AMC_PROF("head", 0.0, 0.0, head_bwd(m.B, cls_top ? 1 : m.T, m.d, m.C, m.has_cls, D.head_ln, dlogits, P(L.head_w),
+                           D.head_ln ? P(L.head_ln_w) : nullptr, w.hl, w.hxhat, w.hrstd, w.dhl,
+                           cls_top ? w.c.dy32 : w.dy32,
                            grads + L.head_w, grads + L.head_b, D.head_ln ? grads + L.head_ln_w : nullptr,
                            D.head_ln ? grads + L.head_ln_b : nullptr, st));
           if (denc_out) {
@@ -475,7 +599,7 @@ struct Model {
           AMC_CUDA(cudaMemcpyAsync(w.dy32, denc_out, nx * 4, cudaMemcpyDeviceToDevice, st));
         }
       } else if (s <= m.L) {
-        AMC_TRY(layer_bwd(m.L - s, grads));
+        AMC_TRY(layer_bwd(m.L - s, grads, cls_top && s == 1));
       } else {
         // embedding front end: dcls, dW_emb, db_emb (input never needs a gradient: Appendix B)
         if (m.has_cls) AMC_PROF("frontend_bwd_misc", 0.0, 0.0, cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
