@@ -141,6 +141,11 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
                         float max_norm, float grad_scale, int64_t step, float* norm_ws,
                         amc_stream_t stream);
 
+/* Dataset-level normalisation statistics on the device (R/dataloader/dataset.py:115-157): for interleaved
+ * frames x [n_frames, frame_len, 2] fp32, acc4 (device, fp64, zeroed by the caller) += {sum I, sum I^2, sum Q,
+ * sum Q^2}.  mean = s/n, unbiased std = sqrt((ss - s^2/n)/(n-1)), floored at 1e-8 like the reference. */
+int amc_iq_stats(int64_t n_frames, int64_t frame_len, const float* x, double* acc4, amc_stream_t stream);
+
 /* ---- operator-level calls (used by the block tests; the whole-path calls are built from
  *      the same kernels) ------------------------------------------------------------- */
 

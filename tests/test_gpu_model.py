@@ -165,3 +165,14 @@ def test_batch_sizes_and_eval_determinism():
             assert y1.shape == (B, 11)
             assert torch.equal(y1, y2)
         assert model(torch.zeros(0, 2, 1024, device=DEV)).shape == (0, 11)
+
+
+def test_device_norm_stats_match_dataset_statistics():
+    """R/dataloader/dataset.py:115-157 statistics, computed on the device (fp64 accumulation)."""
+    from vit_vs_raw_iq_b200 import _lib
+    rng = np.random.default_rng(3)
+    raw = (rng.standard_normal((300, 1024, 2)) * np.array([0.76, 0.77]) + np.array([-0.0007, 0.0031])).astype(np.float32)
+    ref = O.normalization_stats(raw)
+    got = _lib.device_norm_stats(torch.from_numpy(raw).to(DEV))
+    for k in ref:
+        assert abs(got[k] - ref[k]) < 1e-6, (k, got[k], ref[k])

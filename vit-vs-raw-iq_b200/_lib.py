@@ -61,6 +61,7 @@ def _load():
         "amc_model_bwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, i32, i32, vp],
         "amc_ce_loss": [i32, i32, vp, vp, f32, f32, f32, vp, vp, vp],
         "amc_adamw_clip_step": [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, i64, vp, vp],
+        "amc_iq_stats": [i64, i64, vp, vp, vp],
         "amc_gemm": [i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, vp, i32, i32, vp],
         "amc_gemm_ln": [i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
         "amc_gemm_relu_mask": [i32, i32, i32, vp, i32, vp, i32, vp, f32, vp, vp],
@@ -122,4 +123,24 @@ def profile_dump() -> dict:
     for line in buf.value.decode().splitlines():
         name, n, ms, fl, by = line.split()
         out[name] = dict(n=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out
+
+
+def device_norm_stats(x) -> dict:
+    """i_mean / i_std / q_mean / q_std of device-resident interleaved frames [N, L, 2] (fp32), computed on the
+    GPU with fp64 accumulation (the reference subsamples <= 5000 frames on the host: dataset.py:115-157)."""
+    import torch
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3 and x.shape[2] == 2):
+        raise RuntimeError("device_norm_stats expects a contiguous CUDA float32 tensor [N, L, 2]")
+    acc = torch.zeros(4, dtype=torch.float64, device=x.device)
+    check(lib.amc_iq_stats(x.shape[0], x.shape[1], x.data_ptr(), acc.data_ptr(),
+                           torch.cuda.current_stream(x.device).cuda_stream), "amc_iq_stats")
+    si, ssi, sq, ssq = acc.tolist()
+    n = float(x.shape[0] * x.shape[1])
+    out = {}
+    for name, s1, s2 in (("i", si, ssi), ("q", sq, ssq)):
+        mean = s1 / n
+        var = max((s2 - s1 * s1 / n) / max(n - 1.0, 1.0), 0.0)
+        out[name + "_mean"] = mean
+        out[name + "_std"] = max(var ** 0.5, 1e-8)
     return out

@@ -699,6 +699,12 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
                     step, norm_ws, (cudaStream_t)stream);
 }
 
+int amc_iq_stats(int64_t n_frames, int64_t frame_len, const float* x, double* acc4, amc_stream_t stream) {
+  AMC_CHECK_ARG(n_frames >= 0 && frame_len >= 1 && x && acc4, "bad argument");
+  AMC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7) == 0, "frames must be 8-byte aligned");
+  return iq_stats(n_frames * frame_len, x, acc4, (cudaStream_t)stream);
+}
+
 int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA, const void* B, int ldb, int transB,
              const float* bias, const float* res32, int ldres, int relu, void* D16, int ldd16, float* D32, int ldd32,
              int accumulate, amc_stream_t stream) {

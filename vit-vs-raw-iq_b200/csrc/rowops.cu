@@ -301,6 +301,61 @@ __global__ void __launch_bounds__(256) patchify_kernel(PatchP p, const float* __
   }
 }
 
+// Bandwidth-bound version (K % 8 == 0): one frame at a time is staged in shared memory as a planar,
+// normalised [channel][sample] image with coalesced 128-bit loads (the dataset layout de-interleaves and
+// z-scores on the way in); the patch / segment gather then runs out of shared memory and every thread writes
+// 8 consecutive operand elements as 128-bit stores.  HBM sees each input byte and each output byte once.
+template <typename E>
+__global__ void __launch_bounds__(256) patchify_frames_kernel(PatchP p, const float* __restrict__ src,
+                                                              E* __restrict__ A) {
+  extern __shared__ __align__(16) float plane[];          // [in_ch_eff][n_per_ch]
+  const int n_per_ch = p.kind == AMC_KIND_RAWIQ ? p.seq_len : p.img_h * p.img_w;
+  const int raw = p.input_layout == AMC_INPUT_RAW;
+  // dataset layout: 2 planes of L samples (raw-IQ: L = seq_len; ViT: L = H*W/2 and the image is cat(I, Q))
+  const int L = raw ? (p.kind == AMC_KIND_RAWIQ ? p.seq_len : p.img_h * p.img_w / 2) : 0;
+  const int total = raw ? 2 * L : p.in_ch * n_per_ch;    // floats per frame
+  const int groups = p.Ttok * p.K / 8;                    // 8-element output groups per frame
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* fsrc = src + (size_t)b * total;
+    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(fsrc) + i);
+      if (raw) {      // (I, Q, I, Q) -> planar + z-score (dataset.py:215-217)
+        const int n = 2 * i;
+        plane[n] = (v.x - p.mean[0]) * p.inv_std[0];
+        plane[L + n] = (v.y - p.mean[1]) * p.inv_std[1];
+        plane[n + 1] = (v.z - p.mean[0]) * p.inv_std[0];
+        plane[L + n + 1] = (v.w - p.mean[1]) * p.inv_std[1];
+      } else {
+        *reinterpret_cast<float4*>(plane + 4 * i) = v;
+      }
+    }
+    __syncthreads();
+    E* arow = A + (size_t)b * p.Ttok * p.K;
+    for (int gI = threadIdx.x; gI < groups; gI += blockDim.x) {
+      const int e0 = gI * 8, t = e0 / p.K, k0 = e0 - t * p.K;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        int idx;
+        if (p.kind == AMC_KIND_RAWIQ) {
+          const int c = k / p.seg, sidx = k - c * p.seg;
+          idx = c * p.seq_len + t * p.seg + sidx;          // dataset layout: plane c == channel c
+        } else {
+          const int pp = p.patch * p.patch, wp = p.img_w / p.patch;
+          const int c = k / pp, rem = k - c * pp, r = rem / p.patch, cc = rem - r * p.patch;
+          const int ph = t / wp, pw = t - ph * wp;
+          idx = c * p.img_h * p.img_w + (ph * p.patch + r) * p.img_w + pw * p.patch + cc;   // cat(I,Q) == planar
+        }
+        v[j] = plane[idx];
+      }
+      store4(arow + e0, make_float4(v[0], v[1], v[2], v[3]));
+      store4(arow + e0 + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    __syncthreads();
+  }
+}
+
 // CLS rows of x0: x0[b,0,:] = dropout(cls + pos[0])   (encoder.py:104-111)
 template <typename E>
 __global__ void cls_rows_kernel(int B, int T, int d, const float* __restrict__ cls, const float* __restrict__ pos,
@@ -644,6 +699,32 @@ __global__ void __launch_bounds__(256) adamw_kernel(int64_t n, float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Dataset normalisation statistics (R/dataloader/dataset.py:115-157): sums and sums of squares of the I and Q
+// channels of interleaved frames, fp64 accumulation, one atomic per block.  acc = {sum I, sum I^2, sum Q, sum Q^2}
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iq_stats_kernel(int64_t n_pairs, const float2* __restrict__ x,
+                                                       double* __restrict__ acc) {
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = __ldg(x + i);
+    s[0] += v.x; s[1] += (double)v.x * v.x; s[2] += v.y; s[3] += (double)v.y * v.y;
+  }
+  __shared__ double red[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
 }  // namespace
 
 // ---- host launchers ---------------------------------------------------------------------
@@ -731,8 +812,23 @@ template <typename E>
 int patchify(const AmcDesc& D, int Ttok, int K, const float* src, E* A, cudaStream_t st) {
   const size_t total = (size_t)D.B * Ttok * K;
   if (total == 0) return 0;
+  const PatchP pp = make_patchp(D, Ttok, K);
+  const bool raw = D.input_layout == AMC_INPUT_RAW;
+  const int n_per_ch = D.kind == AMC_KIND_RAWIQ ? D.seq_len : D.img_h * D.img_w;
+  const int frame_floats = raw ? (D.kind == AMC_KIND_RAWIQ ? 2 * D.seq_len : D.img_h * D.img_w) : D.in_ch * n_per_ch;
+  const size_t smem = (size_t)frame_floats * sizeof(float);
+  const bool covers = raw || (size_t)Ttok * K == (size_t)frame_floats;      // every input sample is embedded
+  if (K % 8 == 0 && frame_floats % 4 == 0 && smem <= 96 * 1024 && covers &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    if (smem > 48 * 1024)
+      AMC_CUDA(cudaFuncSetAttribute(patchify_frames_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    const int blocks = std::min(D.B, 148 * 8);
+    patchify_frames_kernel<E><<<blocks, 256, smem, st>>>(pp, src, A);
+    AMC_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  patchify_kernel<E><<<blocks, 256, 0, st>>>(make_patchp(D, Ttok, K), src, A);
+  patchify_kernel<E><<<blocks, 256, 0, st>>>(pp, src, A);
   AMC_LAUNCH_CHECK();
   return 0;
 }
@@ -840,6 +936,14 @@ int adamw_clip(int64_t n, float* p, float* g, float* m, float* v, float lr, floa
   const float bc1 = 1.f - (float)pow((double)b1, (double)step);
   const float bc2 = (float)sqrt(1.0 - pow((double)b2, (double)step));
   adamw_kernel<<<blocks, 256, 0, st>>>(n, p, g, m, v, lr, b1, b2, eps, wd, max_norm, grad_scale, bc1, bc2, ws);
+  AMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int iq_stats(int64_t n_pairs, const float* x, double* acc, cudaStream_t st) {
+  if (n_pairs <= 0) return 0;
+  const int blocks = (int)std::min<int64_t>((n_pairs + 255) / 256, 148 * 8);
+  iq_stats_kernel<<<blocks, 256, 0, st>>>(n_pairs, reinterpret_cast<const float2*>(x), acc);
   AMC_LAUNCH_CHECK();
   return 0;
 }
