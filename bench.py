@@ -41,6 +41,24 @@ WORKLOADS = {
     "vit_p4_d128_L6": dict(kind="vit", batch=1024, lr=1e-4, wd=1e-3,
                            kw=dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=4, num_classes=19,
                                    d_model=128, n_head=8, n_layers=6, ffn_hidden=512, drop_prob=0.1)),
+    # BASELINE.json configs[2]: raw-IQ across SPS modes, d256 h8 L6 F1024
+    "rawiq_sps1_seg8_d256_L6": dict(kind="rawiq", batch=1024, lr=1e-4, wd=1e-4, sps=1,
+                                    kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=256, n_head=8,
+                                            n_layers=6, ffn_hidden=1024, drop_prob=0.2, use_cls_token=True,
+                                            embedding_type="segment", segment_size=8)),
+    "rawiq_sps2_seg16_d256_L6": dict(kind="rawiq", batch=1024, lr=1e-4, wd=1e-4, sps=2,
+                                     kw=dict(in_channels=2, seq_length=2048, num_classes=11, d_model=256, n_head=8,
+                                             n_layers=6, ffn_hidden=1024, drop_prob=0.2, use_cls_token=True,
+                                             embedding_type="segment", segment_size=16)),
+    "rawiq_sps2_seg8_d256_L6": dict(kind="rawiq", batch=512, lr=1e-4, wd=1e-4, sps=2,
+                                    kw=dict(in_channels=2, seq_length=2048, num_classes=11, d_model=256, n_head=8,
+                                            n_layers=6, ffn_hidden=1024, drop_prob=0.2, use_cls_token=True,
+                                            embedding_type="segment", segment_size=8)),
+    # BASELINE.json configs[4] corner: the largest point of the hyper-parameter grid (d512, 12 layers, F=4d)
+    "rawiq_seg16_d512_L12": dict(kind="rawiq", batch=1024, lr=1e-4, wd=1e-4,
+                                 kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=512, n_head=8,
+                                         n_layers=12, ffn_hidden=2048, drop_prob=0.2, use_cls_token=True,
+                                         embedding_type="segment", segment_size=16)),
 }
 DEFAULT_WORKLOAD = "vit_p16_d256_L6"
 
@@ -120,41 +138,64 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the numpy oracle (a port of the reference's algorithm) on the host cores
+# Reference arm / CPU baseline: the PyTorch-eager port of the reference path (oracle/amc_torch_port.py:
+# the same ATen operators the reference's modules issue, dropout included) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_port_train_frames_per_s(w, sample_frames, steps, warmup):
-    import numpy as np
+def port_setup(w, sample_frames, device="cpu", seed=0):
+    import torch
     from oracle import amc_oracle as O
+    from oracle import amc_torch_port as TP
     kw = {k: v for k, v in w["kw"].items() if k != "drop_prob"}
     cfg = O.Config(kind=w["kind"], **kw)
-    params = O.init_params(cfg, 0)
-    rng = np.random.default_rng(0)
+    params = TP.make_params(cfg, seed, device)
+    g = torch.Generator().manual_seed(seed)
     shape = (sample_frames, 1, 32, 64) if w["kind"] == "vit" else (sample_frames, 2, kw["seq_length"])
-    src = rng.standard_normal(shape).astype(np.float32)
-    labels = rng.integers(0, cfg.num_classes, sample_frames)
-    pk = [k for k in params if k not in O.BUFFER_KEYS]
-    m = {k: np.zeros_like(params[k]) for k in pk}
-    v = {k: np.zeros_like(params[k]) for k in pk}
+    src = torch.randn(shape, generator=g).to(device)
+    labels = torch.randint(0, cfg.num_classes, (sample_frames,), generator=g).to(device)
+    ts = TP.TrainStep(params, cfg, drop_prob=w["kw"]["drop_prob"], lr=w["lr"], weight_decay=w["wd"],
+                      betas=(0.9, 0.99), max_norm=1.0, label_smoothing=0.1)
+    return ts, src, labels
+
+
+def cpu_port_train_frames_per_s(w, sample_frames, steps, warmup):
+    """Train steps of the torch port on all host threads -> (frames/s, s/step, threads)."""
+    import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    ts, src, labels = port_setup(w, sample_frames)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        _, _, g = O.loss_and_grads(src, labels, params, cfg, 0.1)
-        _, g = O.clip_grad_norm(g, 1.0)
-        p2, m, v = O.adamw_step(params, g, m, v, it + 1, w["lr"], (0.9, 0.99), 1e-8, w["wd"])
-        params.update(p2)
+        loss, _, _ = ts.step(src, labels)
+        loss.item()                                   # the reference reads loss.item() every step
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return sample_frames * len(times) / sum(times), sum(times) / len(times)
+    return sample_frames * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
 
 
-def host_threads():
+def gpu_eager_port_frames_per_s(w, frames, dev, steps=5, warmup=2):
+    """The same port in PyTorch eager on the GPU (TF32 on, as R/training/train.py:359-360 sets it)."""
+    import torch
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
     try:
-        from threadpoolctl import threadpool_info
-        import numpy  # noqa: F401
-        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
-        return max(n) if n else 1
-    except Exception:
-        return os.cpu_count() or 1
+        ts, src, labels = port_setup(w, frames, dev)
+        for _ in range(warmup):
+            ts.step(src, labels)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, _, _ = ts.step(src, labels)
+            loss.item()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        del ts, src, labels
+        torch.cuda.empty_cache()
+    return frames / (ms / 1e3), ms
 
 
 def run_reference_arm(args, w, wname):
@@ -162,16 +203,16 @@ def run_reference_arm(args, w, wname):
     if rank != 0:
         return
     sample = args.cpu_sample
-    fps, sec = cpu_port_train_frames_per_s(w, sample, args.steps, max(args.warmup, 1))
-    cores = host_threads()
+    fps, sec, cores = cpu_port_train_frames_per_s(w, sample, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wname, "frames_per_step": sample, "note":
-                   "CPU numpy port (oracle/) of the reference train step, dropout omitted (favours the CPU arm)"},
+                   "PyTorch-eager CPU port (oracle/amc_torch_port.py) of the reference train step: same ATen operators, "
+                   "dropout on, fp32, all host threads"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} train steps of {sample} frames, numpy/BLAS on {cores} threads"},
+                         "sample": f"{args.steps} train steps of {sample} frames, torch CPU eager on {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -189,6 +230,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="frames per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -225,7 +267,10 @@ def main():
     # synthetic dataset-layout frames [n, 1024, 2]; a small pool is tiled to the batch (content does not
     # change the arithmetic; a 64 MB batch is far larger than... the activations it produces are >> L2)
     pool_n = 2048
-    X, y, _ = synth.make_frames(pool_n, classes=classes, seed=42 + rank)
+    sps = w.get("sps", 1)
+    if sps > 1:
+        pool_n = 1024
+    X, y, _ = synth.make_frames(pool_n, classes=classes, sps=sps, seed=42 + rank)
     stats = synth.normalization_stats(X)
     model.set_raw_input(stats)
     n_batches = 3
@@ -347,7 +392,7 @@ def main():
                    **{k: kw[k] for k in ("d_model", "n_head", "n_layers", "ffn_hidden", "num_classes", "drop_prob")},
                    "parallelism": f"dp{world}", "optimizer": "clip1.0+AdamW", "label_smoothing": 0.1,
                    "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; 3 batches rotate",
-                   "input": "raw [B,1024,2] fp32 frames, z-score+framing fused in the front end"},
+                   "input": f"raw [B,{X.shape[1]},2] fp32 frames, z-score+framing fused in the front end"},
         "model_tflops": train_fps * 3 * fl_frame / 1e12,
         "model_tflops_frac_of_bf16_peak": train_fps * 3 * fl_frame / 1e12 / (peaks["tf_sustained"] * world),
         "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
@@ -362,15 +407,21 @@ def main():
         "kernel_ms_per_step": classes_ms,
         "train_loss": loss, "train_acc": acc,
     }
+    if world == 1 and not args.no_gpu_eager:
+        del trainer, pipe, hp, model
+        torch.cuda.empty_cache()
+        ef, ems = gpu_eager_port_frames_per_s(w, min(B, w.get("eager_batch", B)), dev)
+        line["gpu_eager_port"] = {"value": ef, "unit": "frames/s", "ms_per_step": ems, "note":
+                                  "the reference's operator sequence in PyTorch eager on this GPU (TF32 on as the "
+                                  "reference sets it, fp32 weights, dropout on); reported beside, not the target"}
     if not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        fps, sec = cpu_port_train_frames_per_s(w, args.cpu_sample, 2, 1)
+        fps, sec, cores = cpu_port_train_frames_per_s(w, args.cpu_sample, 2, 1)
         n_steps = max(2, min(40, int(12.0 / max(sec, 1e-3))))
-        fps, sec = cpu_port_train_frames_per_s(w, args.cpu_sample, n_steps, 1)
-        cores = host_threads()
+        fps, sec, cores = cpu_port_train_frames_per_s(w, args.cpu_sample, n_steps, 1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_steps} train steps of {args.cpu_sample} frames (numpy oracle port, "
-                                          f"no dropout), {time.perf_counter() - t0:.0f} s total"}
+                                "sample": f"{n_steps} train steps of {args.cpu_sample} frames (torch CPU eager port of "
+                                          f"the reference ops, dropout on, fp32), {time.perf_counter() - t0:.0f} s total"}
     print(json.dumps(line), flush=True)
     if args.profile_out:
         with open(args.profile_out, "w") as f:

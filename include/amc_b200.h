@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AMC_ABI_VERSION 3
+#define AMC_ABI_VERSION 4
 
 enum { AMC_KIND_RAWIQ = 0, AMC_KIND_VIT = 1 };
 enum { AMC_F32 = 0, AMC_BF16 = 1 };
@@ -173,9 +173,14 @@ int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* 
 /* softmax(q k^T / sqrt(dh)) v for every (frame, head); qkv is [B*T, 3d] (q | k | v column blocks,
  * head hh = columns hh*dh..), out is [B*T, d] with heads concatenated
  * (multi_head_attention.py:34-47 + scale_dot_product_attention.py:26-37; mask is always None). */
-int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream);
-int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv,
+/*   lse  (nullable, fp32 [B, h, T]): log2-domain softmax row statistics max*c + log2(sum), c = log2(e)/sqrt(dh);
+ *        written by the forward when given (training) and read by the backward together with `out`.
+ *   out / lse may be NULL in backward (P is then recomputed with its row statistics);
+ *   dbias (nullable, fp32 [3d]): += column sums of dqkv = gradients of the q | k | v biases. */
+int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, float* lse,
                       amc_stream_t stream);
+int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* out, const float* lse,
+                      const void* dout, void* dqkv, float* dbias, amc_stream_t stream);
 
 /* y = gamma * (u - mean) / sqrt(var_biased + eps) + beta over the last dim (layers_norm.py:11-19).
  *   u fp32 [M,d]; y16 (dtype) / y32 (fp32) / xhat (dtype) / rstd (fp32 [M]) may each be NULL. */

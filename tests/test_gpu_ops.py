@@ -97,17 +97,24 @@ def test_gemm_wgrad_split_k(dt, M, N, K):
                                       (2, 16, 2, 24), (1, 1, 2, 16), (4, 16, 4, 16), (5, 13, 2, 64), (3, 9, 4, 16),
                                       (50, 9, 8, 32), (7, 5, 8, 32), (3, 65, 8, 16), (2, 129, 8, 16), (2, 129, 8, 32),
                                       (2, 100, 4, 64), (4, 33, 8, 32), (1, 288, 2, 16), (3, 48, 4, 32), (2, 257, 16, 16)])
+@pytest.mark.parametrize("saved", [True, False])
 @pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
-def test_attention_fwd_bwd(dt, B, T, h, dh):
+def test_attention_fwd_bwd(dt, B, T, h, dh, saved):
+    """saved=True: the training path (forward keeps lse, backward reads out + lse and also emits the q|k|v bias
+    gradients); saved=False: backward recomputes the row statistics (out / lse / dbias = NULL)."""
     d = h * dh
     g = torch.Generator(device=DEV).manual_seed(T * 31 + dh)
     qkv = torch.randn(B * T, 3 * d, device=DEV, generator=g).to(tdtype(dt))
     dout = torch.randn(B * T, d, device=DEV, generator=g).to(tdtype(dt))
     out = torch.empty(B * T, d, device=DEV, dtype=tdtype(dt))
     dqkv = torch.empty(B * T, 3 * d, device=DEV, dtype=tdtype(dt))
-    _lib.check(_lib.lib.amc_attention_fwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr(), stream()))
-    _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
-                                          stream()))
+    lse = torch.full((B, h, T), float("nan"), device=DEV)
+    dbias = torch.zeros(3 * d, device=DEV)
+    _lib.check(_lib.lib.amc_attention_fwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr(),
+                                          lse.data_ptr() if saved else None, stream()))
+    _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr() if saved else None,
+                                          lse.data_ptr() if saved else None, dout.data_ptr(), dqkv.data_ptr(),
+                                          dbias.data_ptr() if saved else None, stream()))
     torch.cuda.synchronize()
     x = qkv.double().requires_grad_(True)
     q, k, v = [t.view(B, T, h, dh).transpose(1, 2) for t in x.view(B, T, 3 * d).split(d, dim=-1)]
@@ -117,6 +124,10 @@ def test_attention_fwd_bwd(dt, B, T, h, dh):
     tol = 1e-5 if dt == _lib.F32 else 2e-2
     assert relerr(out.float(), ref.detach()) < tol
     assert relerr(dqkv.float(), x.grad) < tol * (1 if dt == _lib.F32 else 1.5)
+    if saved:
+        ref_b = x.grad.sum(0)
+        # the k-bias gradient is identically zero: absolute bound relative to the others
+        assert (dbias.double() - ref_b).abs().max() < (1e-4 if dt == _lib.F32 else 3e-2) * ref_b.abs().max()
 
 
 @pytest.mark.parametrize("M,d", [(1000, 128), (77, 256), (513, 512), (64, 16), (33, 96)])

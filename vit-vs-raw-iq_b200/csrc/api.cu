@@ -122,6 +122,7 @@ int make_layout(const AmcDesc& D, const Dims& m, AmcParamLayout& L) {
 struct LayerBuf {
   void *qkv, *o, *xhat1, *x1_16, *hid, *xhat2;
   float *rstd1, *x1_32, *rstd2;
+  float* lse;   // [B, h, T] softmax row statistics (training, bf16 tile attention)
 };
 struct Work {
   bf16* w16 = nullptr;   // bf16 copy of the parameter blob
@@ -182,9 +183,11 @@ void carve(const AmcDesc& D, const Dims& m, const AmcParamLayout& L, char* base,
       b.xhat2 = take(M * d * e);
       b.rstd1 = (float*)take(M * 4);
       b.rstd2 = (float*)take(M * 4);
+      b.lse = (float*)take(M * m.h * 4);
     } else {
       b.xhat1 = b.xhat2 = nullptr;
       b.rstd1 = b.rstd2 = nullptr;
+      b.lse = nullptr;
     }
   }
   w.u32 = (float*)take(M * d * 4);
@@ -384,7 +387,7 @@ struct Model {
     g.epi.bias = PL(l, L.bq); g.epi.D16 = b.qkv; g.epi.ldd16 = 3 * d;
     AMC_TRY(gemm<E>(g, st));
     ProfScope ps("attn_fwd", st, 4.0 * m.M * m.T * d, (double)M * 4 * d * sizeof(E));
-    AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, st));
+    AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, b.lse, st));
     return 0;
   }
 
@@ -558,7 +561,7 @@ struct Model {
     }
     {
       ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
-      AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)w.dO, (E*)w.dqkv, G + L.bq, st));
+      AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)b.o, b.lse, (const E*)w.dO, (E*)w.dqkv, G + L.bq, st));
     }
     AMC_TRY(wgrad(3 * d, d, w.dqkv, 3 * d, w.x16[l], d, G + L.wq, nullptr));
     // dgrad QKV + skip -> gradient w.r.t. the layer input
@@ -740,17 +743,21 @@ int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* 
   return gemm_bf16(g, (cudaStream_t)stream);
 }
 
-int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream) {
-  AMC_CHECK_ARG(qkv && out, "NULL argument");
-  if (dtype == AMC_BF16) return attention_fwd<bf16>(B, T, h, dh, (const bf16*)qkv, (bf16*)out, (cudaStream_t)stream);
-  return attention_fwd<float>(B, T, h, dh, (const float*)qkv, (float*)out, (cudaStream_t)stream);
-}
-int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv,
+int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, float* lse,
                       amc_stream_t stream) {
+  AMC_CHECK_ARG(qkv && out, "NULL argument");
+  if (dtype == AMC_BF16)
+    return attention_fwd<bf16>(B, T, h, dh, (const bf16*)qkv, (bf16*)out, lse, (cudaStream_t)stream);
+  return attention_fwd<float>(B, T, h, dh, (const float*)qkv, (float*)out, lse, (cudaStream_t)stream);
+}
+int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* out, const float* lse,
+                      const void* dout, void* dqkv, float* dbias, amc_stream_t stream) {
   AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
   if (dtype == AMC_BF16)
-    return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, nullptr, (cudaStream_t)stream);
-  return attention_bwd<float>(B, T, h, dh, (const float*)qkv, (const float*)dout, (float*)dqkv, nullptr, (cudaStream_t)stream);
+    return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)dout, (bf16*)dqkv, dbias,
+                               (cudaStream_t)stream);
+  return attention_bwd<float>(B, T, h, dh, (const float*)qkv, (const float*)out, lse, (const float*)dout, (float*)dqkv,
+                              dbias, (cudaStream_t)stream);
 }
 
 int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamma, const float* beta, float eps,

@@ -1271,7 +1271,7 @@ inline int pick_warps(int T) { return std::max(1, std::min(8, (T + 7) / 8)); }
 }  // namespace
 
 template <typename E>
-int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_t st) {
+int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse, cudaStream_t st) {
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
@@ -1293,6 +1293,11 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
       AMC_LAUNCH_CHECK();
       return 0;
     }
+  }
+  if constexpr (std::is_same<E, bf16>::value) {
+    bool handled = false;
+    AMC_TRY(attn_tiles_fwd(B, T, h, dh, qkv, out, lse, &handled, st));
+    if (handled) return 0;
   }
   if constexpr (std::is_same<E, bf16>::value) {
     if (use_tc(T, h, dh)) {
@@ -1353,12 +1358,12 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_
   AMC_LAUNCH_CHECK();
   return 0;
 }
-template int attention_fwd<float>(int, int, int, int, const float*, float*, cudaStream_t);
-template int attention_fwd<bf16>(int, int, int, int, const bf16*, bf16*, cudaStream_t);
+template int attention_fwd<float>(int, int, int, int, const float*, float*, float*, cudaStream_t);
+template int attention_fwd<bf16>(int, int, int, int, const bf16*, bf16*, float*, cudaStream_t);
 
 template <typename E>
-int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, bool* fused,
-                       cudaStream_t st) {
+int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* out, const float* lse, const E* dout, E* dqkv,
+                       float* dbias, bool* fused, cudaStream_t st) {
   *fused = false;
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
@@ -1379,6 +1384,14 @@ int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* dout,
       else AMC_LAUNCH_MMA_BWD(4);
 #undef AMC_LAUNCH_MMA_BWD
       AMC_LAUNCH_CHECK();
+      *fused = true;
+      return 0;
+    }
+  }
+  if constexpr (std::is_same<E, bf16>::value) {
+    bool handled = false;
+    AMC_TRY(attn_tiles_bwd(B, T, h, dh, qkv, out, lse, dout, dqkv, dbias, &handled, st));
+    if (handled) {
       *fused = true;
       return 0;
     }
@@ -1447,13 +1460,16 @@ int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* dout,
 // dbias (nullable): += column sums of dqkv, i.e. the gradient of the q/k/v biases.  The tensor-core kernel
 // produces it from its staged rows; the other kernels are followed by a column-sum pass.
 template <typename E>
-int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, cudaStream_t st) {
+int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* out, const float* lse, const E* dout, E* dqkv,
+                  float* dbias, cudaStream_t st) {
   bool fused = false;
-  AMC_TRY(attention_bwd_impl<E>(B, T, h, dh, qkv, dout, dqkv, dbias, &fused, st));
+  AMC_TRY(attention_bwd_impl<E>(B, T, h, dh, qkv, out, lse, dout, dqkv, dbias, &fused, st));
   if (dbias && !fused) AMC_TRY(colsum<E>(B * T, 3 * h * dh, dqkv, 3 * h * dh, dbias, st));
   return 0;
 }
-template int attention_bwd<float>(int, int, int, int, const float*, const float*, float*, float*, cudaStream_t);
-template int attention_bwd<bf16>(int, int, int, int, const bf16*, const bf16*, bf16*, float*, cudaStream_t);
+template int attention_bwd<float>(int, int, int, int, const float*, const float*, const float*, const float*, float*,
+                                  float*, cudaStream_t);
+template int attention_bwd<bf16>(int, int, int, int, const bf16*, const bf16*, const float*, const bf16*, bf16*, float*,
+                                 cudaStream_t);
 
 }  // namespace amc

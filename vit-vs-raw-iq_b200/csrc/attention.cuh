@@ -6,8 +6,17 @@
 #include "common.cuh"
 
 namespace amc {
+// lse (nullable, [B, h, T] fp32): log2-domain softmax row statistics written by the forward tile kernel and read
+// by its backward together with `out` (both nullable in backward: the older two-phase kernels are used then).
 template <typename E>
-int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, cudaStream_t st);
+int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse, cudaStream_t st);
 template <typename E>
-int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* dout, E* dqkv, float* dbias, cudaStream_t st);
+int attention_bwd(int B, int T, int h, int dh, const E* qkv, const E* out, const float* lse, const E* dout, E* dqkv,
+                  float* dbias, cudaStream_t st);
+
+// attn_tiles.cu: TMA-tiled single-CTA kernels for 16 < T <= 288 (bf16); *handled = false -> caller falls back
+bool attn_tiles_supported(int T, int h, int dh);
+int attn_tiles_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float* lse, bool* handled, cudaStream_t st);
+int attn_tiles_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out, const float* lse, const bf16* dout,
+                   bf16* dqkv, float* dbias, bool* handled, cudaStream_t st);
 }  // namespace amc
