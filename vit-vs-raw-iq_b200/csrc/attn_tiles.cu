@@ -236,8 +236,7 @@ attn_tile_fwd_kernel(const __grid_constant__ CUtensorMap mQKV, const __grid_cons
   if (tid == 0) {
     tma_prefetch_desc(&mQKV);
     tma_prefetch_desc(&mO);
-    mbar_init(full, 1);
-    mbar_init(full + 1, 1);
+    for (int k = 0; k < gm.nst; ++k) mbar_init(full + k, 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -252,14 +251,19 @@ attn_tile_fwd_kernel(const __grid_constant__ CUtensorMap mQKV, const __grid_cons
                       bx * gm.BR, b);
     }
   };
-  if (tid == 0 && (int)blockIdx.x < gm.units) issue(blockIdx.x, 0);
+  // input ring of nst stages: the copies of unit i + nst - 1 are issued at the top of iteration i, into the stage
+  // iteration i - 1 has just finished reading (nst = 1: after this iteration's own barrier instead)
+  const int ahead = gm.nst - 1;
+  if (tid == 0)
+    for (int k = 0; k < max(ahead, 1); ++k)
+      if ((int)blockIdx.x + k * (int)gridDim.x < gm.units) issue(blockIdx.x + k * gridDim.x, k);
   const int last_k0 = ((NQ - 1) / NBC) * NBC;      // first block of the final chunk
-  int i = 0;
+  int i = 0, s = 0;
+  uint32_t ph = 0;
   for (int u = blockIdx.x; u < gm.units; u += gridDim.x, ++i) {
-    const int s = gm.nst == 2 ? (i & 1) : 0;
     const int b = u / gm.ngrp, hg = u - b * gm.ngrp;
-    if (gm.nst == 2 && tid == 0 && u + (int)gridDim.x < gm.units) issue(u + gridDim.x, s ^ 1);
-    mbar_wait(full + s, gm.nst == 2 ? ((i >> 1) & 1) : (i & 1));
+    if (ahead > 0 && tid == 0 && u + ahead * (int)gridDim.x < gm.units) issue(u + ahead * gridDim.x, (s + ahead) % gm.nst);
+    mbar_wait(full + s, ph);
     const uint32_t so = so_base + (gm.nso == 2 ? (i & 1) : 0) * gm.G * tb;
     for (int item = warp; item < items; item += nw) {
       const int hh = item / NQ, qt = item - hh * NQ;
@@ -302,6 +306,7 @@ attn_tile_fwd_kernel(const __grid_constant__ CUtensorMap mQKV, const __grid_cons
       if (gm.nst == 1 && u + (int)gridDim.x < gm.units) issue(u + gridDim.x, 0);
     }
     if (gm.nso == 1) __syncthreads();
+    if (++s == gm.nst) { s = 0; ph ^= 1; }
   }
   if (tid == 0) bulk_wait_all0();
 }
@@ -665,21 +670,26 @@ int attn_tiles_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, floa
   if (!attn_tiles_supported(T, h, dh)) return 0;
   TileGeom g;
   base_geom(g, B, T, h, dh);
-  // heads per CTA: the smallest divisor of h that gives the warps >= 8 work items, within shared memory
+  // heads per CTA: enough (about two per warp) work items per unit to amortise the per-unit barrier / copy issue,
+  // while two input stages + two output stagings still let two CTAs share an SM; then as many input stages (<= 4) as fit
+  const size_t budget = (SMEM_MAX - 2048) / 2;
   int G = 0;
   for (int c = 1; c <= h; ++c) {
     if (h % c) continue;
     set_group(g, B, c);
-    g.nst = g.nso = 1;
-    if (fwd_bytes(g) > SMEM_MAX) break;
+    g.nst = 2; g.nso = 2;
+    if (G != 0 && (fwd_bytes(g) > budget || c * g.NQ > 20)) break;
     G = c;
-    if (c * g.NQ >= 8) break;
   }
-  if (G == 0) return 0;
   set_group(g, B, G);
   g.nst = 2; g.nso = 2;
   if (fwd_bytes(g) > SMEM_MAX) { g.nso = 1; }
   if (fwd_bytes(g) > SMEM_MAX) { g.nst = 1; }
+  if (fwd_bytes(g) > SMEM_MAX) return 0;
+  while (g.nst < 4) {
+    ++g.nst;
+    if (fwd_bytes(g) > budget) { --g.nst; break; }
+  }
   const size_t sm = fwd_bytes(g);
   const int threads = 32 * pick_warps(G * g.NQ);
   CUtensorMap mQKV, mO;
@@ -715,13 +725,14 @@ int attn_tiles_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out
   if (!attn_tiles_supported(T, h, dh) || out == nullptr || lse == nullptr) return 0;
   TileGeom g;
   base_geom(g, B, T, h, dh);
+  const size_t budget = (SMEM_MAX - 2048) / 2;
   int G = 0;
   for (int c = 1; c <= h; ++c) {
     if (h % c) continue;
     set_group(g, B, c);
     if (bwd_bytes(g, dh) > SMEM_MAX) break;
+    if (G != 0 && (bwd_bytes(g, dh) > budget || c * g.NQ > 20)) break;
     G = c;
-    if (c * g.NQ >= 8) break;
   }
   if (G == 0) return 0;
   set_group(g, B, G);
