@@ -365,23 +365,47 @@ def main():
     fl_frame = flops_per_frame(w)
     frames = B * world
     train_fps = frames * args.steps / (ms_train / 1e3)
+    tot_ms = sum(v["ms"] for v in prof.values())
+    peak_tf = peaks["tf_sustained"] if args.dtype == "bf16" else None     # fp32 mode runs on the FMA pipe
+
+    def class_roofline(name, v):
+        """Roofline of one kernel class: algorithmic FLOPs / bytes per launch over its CUDA-event time (events are
+        recorded inside the library on the launch stream, amc_profile_enable/dump)."""
+        ms = v["ms"] / max(v["n"], 1)
+        tf = v["flops"] / max(v["ms"], 1e-9) / 1e9
+        gbs = v["bytes"] / max(v["ms"], 1e-9) / 1e6
+        t_tensor = v["flops"] / (peak_tf * 1e12) if peak_tf and v["flops"] else 0.0
+        t_hbm = v["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_tensor > t_hbm else "hbm"
+        r = {"kernel": name, "bound": bound, "launches_per_step": v["n"] / prof_steps, "avg_launch_ms": ms,
+             "share_of_step": v["ms"] / tot_ms if tot_ms else None}
+        if bound == "tensor":
+            r.update(achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf, hbm_GBps=gbs)
+        else:
+            r.update(achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"], tflops=tf)
+        return r
+
+    table = [class_roofline(k, v) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if v["bytes"] or v["flops"]]
+    dom = table[0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # written by tools/ncu_summary.py from `ncu --set full`
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj.get(args.workload, {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
+    roofline = {k: dom[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
+    roofline.update(traffic=traffic, peak_source=peaks["source"] + (" (sustained)" if dom["bound"] == "tensor" else ""),
+                    launches_per_step=dom["launches_per_step"], avg_launch_ms=dom["avg_launch_ms"],
+                    share_of_step=dom["share_of_step"],
+                    algorithmic_per_launch={"flops": prof[dom["kernel"]]["flops"] / max(prof[dom["kernel"]]["n"], 1),
+                                            "bytes": prof[dom["kernel"]]["bytes"] / max(prof[dom["kernel"]]["n"], 1)})
     gemm = {k: v for k, v in prof.items() if k.startswith("gemm")}
     g_ms = sum(v["ms"] for v in gemm.values())
     g_fl = sum(v["flops"] for v in gemm.values())
     g_by = sum(v["bytes"] for v in gemm.values())
-    g_n = sum(v["n"] for v in gemm.values())
-    tot_ms = sum(v["ms"] for v in prof.values())
-    achieved_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    roofline = {
-        "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all call sites)" if args.dtype == "bf16" else
-                  "gemm_simt_kernel (fp32 FMA GEMM)",
-        "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-        "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
-        "launches_per_step": g_n / prof_steps, "avg_launch_ms": g_ms / max(g_n, 1),
-        "share_of_step": g_ms / tot_ms if tot_ms else None,
-        "hbm_view": {"algorithmic_GBps": g_by / (g_ms * 1e-3) / 1e9 if g_ms else 0.0, "peak": peaks["hbm_gbs"],
-                     "frac": (g_by / (g_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if g_ms else 0.0},
-    }
+    roofline["all_gemms"] = {"tflops": g_fl / max(g_ms, 1e-9) / 1e9, "frac_of_tensor_peak": g_fl / max(g_ms, 1e-9) / 1e9 / peaks["tf_sustained"],
+                             "algorithmic_GBps": g_by / max(g_ms, 1e-9) / 1e6,
+                             "frac_of_hbm_peak": g_by / max(g_ms, 1e-9) / 1e6 / peaks["hbm_gbs"],
+                             "share_of_step": g_ms / tot_ms if tot_ms else None}
     classes_ms = {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
     line = {
@@ -404,6 +428,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,
+        "rooflines": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table],
         "kernel_ms_per_step": classes_ms,
         "train_loss": loss, "train_acc": acc,
     }

@@ -319,7 +319,6 @@ struct Model {
 
   int frontend(const float* src, const float* pos) {
     if (m.B == 0) return 0;
-    AMC_PROF("patchify", 0.0, (double)m.B * m.Ttok * m.K * (4 + sizeof(E)), patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
     GemmArgs g;
     g.M = m.B * m.Ttok; g.N = m.d; g.K = m.K;
     g.A = w.Apatch; g.lda = m.K;
@@ -331,7 +330,21 @@ struct Model {
     g.epi.drop = drop; g.epi.drop_site = site_pe();
     g.epi.D16 = w.x16[0]; g.epi.ldd16 = m.d;
     if (sizeof(E) == 2) { g.epi.D32 = w.x32[0]; g.epi.ldd32 = m.d; }
-    AMC_TRY(gemm<E>(g, st));
+    bool fused = false;
+    if (sizeof(E) == 2) {
+      // one kernel: IQ samples -> normalise / frame / patchify in shared memory -> tcgen05 GEMM -> +bias +PE, dropout
+      bf16* aout = D.training ? reinterpret_cast<bf16*>(w.Apatch) : nullptr;
+      AMC_TRY(frontend_fused(D, m.Ttok, m.K, src, reinterpret_cast<const bf16*>(Wemb()), g.epi, aout, true, &fused, st));
+      if (fused) {
+        const double by = (double)m.B * m.Ttok * m.K * 4 + (double)g.M * m.d * 6 + (D.training ? (double)g.M * m.K * 2 : 0.0);
+        ProfScope ps("frontend_fused", st, 2.0 * g.M * g.N * g.K, by);
+        AMC_TRY(frontend_fused(D, m.Ttok, m.K, src, reinterpret_cast<const bf16*>(Wemb()), g.epi, aout, false, &fused, st));
+      }
+    }
+    if (!fused) {
+      AMC_PROF("patchify", 0.0, (double)m.B * m.Ttok * m.K * (4 + sizeof(E)), patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
+      AMC_TRY(gemm<E>(g, st));
+    }
     if (m.has_cls)
       AMC_PROF("cls_rows", 0.0, 0.0, cls_rows<E>(m.B, m.T, m.d, P(L.cls), pos, (E*)w.x16[0], sizeof(E) == 2 ? w.x32[0] : nullptr, drop, st));
     return 0;

@@ -139,4 +139,10 @@ struct GemmArgs {
 int gemm_f32(const GemmArgs& g, cudaStream_t st);   // gemm_simt.cu
 int gemm_bf16(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu (tcgen05)
 
+// frontend_tc.cu: fused normalise + frame + patchify + embedding GEMM (+bias, +PE, dropout) for the bf16 path.
+// *handled = false when the geometry is outside what the fused kernel covers (caller: patchify + gemm);
+// probe_only = true answers that question without launching.
+int frontend_fused(const AmcDesc& D, int Ttok, int K, const float* src, const bf16* W, const Epi& epi, bf16* Aout,
+                   bool probe_only, bool* handled, cudaStream_t st);
+
 }  // namespace amc

@@ -223,6 +223,37 @@ class HostPredictor:
         return self.p_host[k]
 
 
+class GraphPredictor:
+    """The inference loop for a fixed batch shape as ONE CUDA-graph launch: eval forward + argmax are captured
+    once (all kernel parameters, tensor maps and the workspace are static for a fixed shape) and replayed.
+    At the reference's interactive batch sizes (1..256 frames, compare_models.py / evaluate.py) the forward is
+    ~40 short kernels and launch-bound; the replay removes the per-kernel launch and host set-up cost.
+    ``predict`` accepts a device or (pinned) host tensor of the captured shape and returns the static int64 result
+    tensor (valid until the next call)."""
+
+    def __init__(self, model: _AMCBase, src_shape, warmup: int = 2):
+        self.model = model
+        dev = model.flat_parameters().device
+        self.dev = dev
+        self.x = torch.zeros(src_shape, dtype=torch.float32, device=dev)
+        self.out = torch.empty((src_shape[0],), dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # lazy one-time set-up must not happen inside the capture
+            for _ in range(max(warmup, 1)):
+                predict(model, self.x, self.out)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            predict(model, self.x, self.out)
+
+    def predict(self, src: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 @torch.no_grad()
 def predict(model: _AMCBase, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """argmax class per frame (R/training/utils.py:311-317: model.eval(); model(x).max(1))."""
