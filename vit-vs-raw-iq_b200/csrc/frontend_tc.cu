@@ -11,10 +11,11 @@
 // weight W[d, K] is TMA-loaded once per CTA and stays resident; accumulators are double-buffered in TMEM so the
 // epilogue (bias + positional encoding + dropout, CLS-shifted fp32 and bf16 rows) of tile i overlaps tile i+1.
 //
-// Warp roles (448 threads): warp 0 = W loader (TMA), warp 1 = MMA issuer (one thread), warps 2-5 = converters,
-// warps 6-13 = epilogue (two per TMEM lane quadrant).  Bound: HBM (8 B per IQ sample in, 6 B per embedding
+// Warp roles (448 threads): warp 0 = W loader (TMA), warp 1 = MMA issuer (one thread), warps 2-9 = converters,
+// warps 10-13 = epilogue (one per TMEM lane quadrant).  Bound: HBM (8 B per IQ sample in, 6 B per embedding
 // element out); the GEMM (K <= 256) is a small fraction of the tensor pipe.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm_common.cuh"
 #include "rowops.cuh"
@@ -24,7 +25,7 @@ namespace amc {
 namespace {
 
 constexpr int FBM = 128, FBK = 64;
-constexpr int F_NCONV = 4, F_NEPI = 8;
+constexpr int F_NCONV = 8, F_NEPI = 4;
 constexpr int F_THREADS = 64 + 32 * (F_NCONV + F_NEPI);
 constexpr int F_CONV_WARP0 = 2, F_EPI_WARP0 = 2 + F_NCONV;
 constexpr int F_STG_LD = 32;
@@ -34,11 +35,12 @@ struct FrontParams {
   int B, M;               // frames, token rows B * Ttok
   int Ttok, K, d;
   int kb_total;           // ceil(K / 64)
-  int S, L;               // raw-IQ: segment size, samples per frame
+  int S, L, lg_ttok;      // raw-IQ: segment size, samples per frame, log2(tokens per frame)
   int p;                  // ViT: patch size (image is 32 x 64)
   float mean[2], inv_std[2];
   int tiles_m, tiles_n, vec_ok;
   bf16* Aout;             // nullable: the patchified operand [M, K] (training: embedding weight gradient)
+  int dbg;                // AMC_FRONT_DBG experiments: 1 = no input loads, 2 = no output stores, 4 = no pos/bias loads
 };
 
 template <int BN> struct FrontCfg {
@@ -67,98 +69,161 @@ __device__ __forceinline__ uint32_t a_off(int row, int kcol) {
   return (uint32_t)(row * 128 + ((((kcol >> 3) ^ (row & 7)) << 4) | ((kcol & 7) << 1)));
 }
 
-// One converter warp's share of k-block `kb` of the A tile starting at token row m0.  Every iteration is one
-// warp-wide 512-byte load (lane = one float4) followed by the shared-memory scatter of its 4 values.
-__device__ __forceinline__ void convert_block(const FrontParams& p, const float* __restrict__ src, uint32_t sa, int m0,
-                                              int kb, int cw, int lane) {
+// One converter warp's share of k-block `kb` of the A tile starting at token row m0.  The work is a list of
+// warp-wide 512-byte loads (lane = one float4); they are issued FB at a time before any of their values is
+// consumed, so a warp keeps FB * 512 bytes in flight (the scatter's st.shared would otherwise serialise them).
+constexpr int FB = 8;
+
+struct Slot {              // where one float4 of the input lands
+  const float4* src;       // nullptr: out of range (zero fill)
+  int row0, row1, k0, k1;  // raw layouts: (I pair -> row0,k0), (Q pair -> row1,k1); model layouts: 4 values at (row0,k0)
+};
+
+
+__device__ __forceinline__ Slot slot_of(const FrontParams& p, const float* __restrict__ src, int m0, int kb, int wl,
+                                        int lane) {
+  Slot s;
+  s.src = nullptr; s.row0 = s.row1 = 0; s.k0 = s.k1 = 0;
   if (p.kind == AMC_KIND_RAWIQ) {
     const int S = p.S;
     if (p.raw) {
       // tile = 128 * S consecutive (I, Q) pairs of the frame stream; float4 = samples n, n + 1
-      const int nwl = 2 * S;
-      const float4* base = reinterpret_cast<const float4*>(src + (size_t)m0 * S * 2);
-      for (int wl = cw; wl < nwl; wl += F_NCONV) {
-        const int n = wl * 64 + 2 * lane, row = n / S, s = n - row * S;
-        if (m0 + row < p.M) {
-          const float4 v = __ldg(base + wl * 32 + lane);
-          const uint32_t wi = pk((v.x - p.mean[0]) * p.inv_std[0], (v.z - p.mean[0]) * p.inv_std[0]);
-          const uint32_t wq = pk((v.y - p.mean[1]) * p.inv_std[1], (v.w - p.mean[1]) * p.inv_std[1]);
-          sts32(sa + a_off(row, s), wi);
-          sts32(sa + a_off(row, S + s), wq);
-          if (p.Aout) {
-            bf16* ao = p.Aout + (size_t)(m0 + row) * p.K;
-            *reinterpret_cast<uint32_t*>(ao + s) = wi;
-            *reinterpret_cast<uint32_t*>(ao + S + s) = wq;
-          }
-        } else {
-          sts32(sa + a_off(row, s), 0u);
-          sts32(sa + a_off(row, S + s), 0u);
-        }
-      }
+      const int n = wl * 64 + 2 * lane, row = n / S, sidx = n - row * S;
+      s.row0 = s.row1 = row; s.k0 = sidx; s.k1 = S + sidx;
+      if (m0 + row < p.M) s.src = reinterpret_cast<const float4*>(src + (size_t)m0 * S * 2) + wl * 32 + lane;
     } else {
-      // model layout [B, 2, L] (already normalised): per channel 128 * S consecutive samples per frame segment
-      const int nwl = 2 * S;     // S warp-loads (128 floats each) per channel
-      for (int wl = cw; wl < nwl; wl += F_NCONV) {
-        const int c = wl / S, n = (wl - c * S) * 128 + lane * 4, row = n / S, s = n - row * S;
-        const int gr = m0 + row;
-        uint32_t w0 = 0u, w1 = 0u;
-        if (gr < p.M) {
-          const int b = gr / p.Ttok, t = gr - b * p.Ttok;
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * 2 + c) * p.L + (size_t)t * S + s));
-          w0 = pk(v.x, v.y);
-          w1 = pk(v.z, v.w);
-          if (p.Aout) *reinterpret_cast<uint2*>(p.Aout + (size_t)gr * p.K + c * S + s) = make_uint2(w0, w1);
-        }
-        sts64(sa + a_off(row, c * S + s), w0, w1);
+      // model layout [B, 2, L] (already normalised): S warp-loads (128 samples each) per channel
+      const int c = wl / S, n = (wl - c * S) * 128 + lane * 4, row = n / S, sidx = n - row * S, gr = m0 + row;
+      s.row0 = row; s.k0 = c * S + sidx;
+      if (gr < p.M) {
+        const int b = gr / p.Ttok, t = gr - b * p.Ttok;
+        s.src = reinterpret_cast<const float4*>(src + ((size_t)b * 2 + c) * p.L + (size_t)t * S + sidx);
       }
     }
   } else {
     // ViT, image 32 x 64, patch p in {4, 8, 16}: token = ph * (64/p) + pw, k = r * p + cc  (patch_embedding.py:12-14)
-    const int pp = p.p, wp = 64 / pp;
-    const int rpk = min(pp, 64 / pp);              // patch rows r per 64-wide k-block
-    const int fpt = FBM / p.Ttok;                  // frames per tile
-    const int f0 = m0 / p.Ttok;
+    const int pp = p.p, wp = 64 / pp, rpk = min(pp, 64 / pp), f0 = m0 / p.Ttok;
     if (p.raw) {
       // dataset layout: image = cat(I, Q).view(32, 64) -> image rows 0-15 = I samples, 16-31 = Q samples
       // (V/dataloader/dataset.py:216-224); one warp-load = one image row of I and the matching row of Q
-      const int nph = 16 / pp, nwl = fpt * nph * rpk;
-      for (int wl = cw; wl < nwl; wl += F_NCONV) {
-        const int rr = wl % rpk, t2 = wl / rpk, ph = t2 % nph, f = t2 / nph;
-        const int r = kb * rpk + rr, x = 2 * lane, pw = x / pp, cc = x - pw * pp;
-        const int rowI = f * p.Ttok + ph * wp + pw, rowQ = rowI + nph * wp, kcol = rr * pp + cc;
-        uint32_t wi = 0u, wq = 0u;
-        if (f0 + f < p.B) {
-          const int n = (ph * pp + r) * 64 + x;
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)(f0 + f) * 1024 + n) * 2));
-          wi = pk((v.x - p.mean[0]) * p.inv_std[0], (v.z - p.mean[0]) * p.inv_std[0]);
-          wq = pk((v.y - p.mean[1]) * p.inv_std[1], (v.w - p.mean[1]) * p.inv_std[1]);
-          if (p.Aout) {
-            *reinterpret_cast<uint32_t*>(p.Aout + (size_t)(m0 + rowI) * p.K + r * pp + cc) = wi;
-            *reinterpret_cast<uint32_t*>(p.Aout + (size_t)(m0 + rowQ) * p.K + r * pp + cc) = wq;
-          }
-        }
-        sts32(sa + a_off(rowI, kcol), wi);
-        sts32(sa + a_off(rowQ, kcol), wq);
-      }
+      const int nph = 16 / pp;
+      const int rr = wl % rpk, t2 = wl / rpk, ph = t2 % nph, f = t2 / nph;
+      const int r = kb * rpk + rr, x = 2 * lane, pw = x / pp, cc = x - pw * pp;
+      s.row0 = f * p.Ttok + ph * wp + pw; s.row1 = s.row0 + nph * wp; s.k0 = s.k1 = rr * pp + cc;
+      if (f0 + f < p.B) s.src = reinterpret_cast<const float4*>(src + ((size_t)(f0 + f) * 1024 + (ph * pp + r) * 64 + x) * 2);
     } else {
       // model layout [B, 1, 32, 64]: a half-warp reads one image row (64 px), a warp two consecutive selected rows
-      const int nphh = 32 / pp, nir = fpt * nphh * rpk;
-      for (int wl = cw; 2 * wl < nir; wl += F_NCONV) {
-        const int ir = 2 * wl + (lane >> 4);
-        const int rr = ir % rpk, t2 = ir / rpk, phh = t2 % nphh, f = t2 / nphh;
-        const int r = kb * rpk + rr, x = (lane & 15) * 4, pw = x / pp, cc = x - pw * pp;
-        const int row = f * p.Ttok + phh * wp + pw, kcol = rr * pp + cc;
-        if (ir < nir) {
-          uint32_t w0 = 0u, w1 = 0u;
-          if (f0 + f < p.B) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)(f0 + f) * 32 + phh * pp + r) * 64 + x));
-            w0 = pk(v.x, v.y);
-            w1 = pk(v.z, v.w);
-            if (p.Aout) *reinterpret_cast<uint2*>(p.Aout + (size_t)(m0 + row) * p.K + r * pp + cc) = make_uint2(w0, w1);
-          }
-          sts64(sa + a_off(row, kcol), w0, w1);
+      const int nphh = 32 / pp, ir = 2 * wl + (lane >> 4);
+      const int rr = ir % rpk, t2 = ir / rpk, phh = t2 % nphh, f = t2 / nphh;
+      const int r = kb * rpk + rr, x = (lane & 15) * 4, pw = x / pp, cc = x - pw * pp;
+      s.row0 = f * p.Ttok + phh * wp + pw; s.k0 = rr * pp + cc;
+      if (f0 + f < p.B) s.src = reinterpret_cast<const float4*>(src + ((size_t)(f0 + f) * 32 + phh * pp + r) * 64 + x);
+    }
+  }
+  return s;
+}
+
+// number of warp-loads that make up k-block kb of one tile
+__device__ __forceinline__ int warp_loads(const FrontParams& p) {
+  if (p.kind == AMC_KIND_RAWIQ) return 2 * p.S;
+  const int rpk = min(p.p, 64 / p.p), fpt = FBM / p.Ttok;
+  return p.raw ? fpt * (16 / p.p) * rpk : fpt * (32 / p.p) * rpk / 2;
+}
+
+// Per-thread, tile-invariant description of the FB float4s a converter lane handles in every k-block: computed once
+// per kernel (the index arithmetic has runtime divisors), so the per-tile work is one add + bounds test per load.
+struct LaneSlots {
+  int off[FB];          // float offset from the tile's base pointer (k-block 0); < 0: slot unused
+  uint32_t meta[FB];    // row0 | row1 << 8 | k0 << 16 | k1 << 24
+  uint32_t soff[FB];    // byte offsets inside the swizzled A stage: (row0,k0) | (row1,k1) << 16
+  int kb_stride;        // floats added per k-block
+};
+
+__device__ __forceinline__ void make_lane_slots(const FrontParams& p, int cw, int lane, LaneSlots& ls) {
+  const int nwl = warp_loads(p);
+  ls.kb_stride = 0;
+  if (p.kind == AMC_KIND_VIT) {
+    const int rpk = min(p.p, 64 / p.p);
+    ls.kb_stride = p.raw ? rpk * 64 * 2 : rpk * 64;
+  }
+  const int per = (nwl + F_NCONV - 1) / F_NCONV;      // consecutive warp-loads per warp: contiguous DRAM runs
+#pragma unroll
+  for (int j = 0; j < FB; ++j) {
+    const int wl = j < per ? cw * per + j : nwl;
+    ls.off[j] = -1;
+    ls.meta[j] = 0u;
+    ls.soff[j] = 0u;
+    if (wl < nwl) {
+      // base pointer = nullptr + offsets of tile 0 / k-block 0; only the offset part is kept
+      const Slot t = slot_of(p, reinterpret_cast<const float*>(0), 0, 0, wl, lane);
+      ls.meta[j] = (uint32_t)t.row0 | ((uint32_t)t.row1 << 8) | ((uint32_t)t.k0 << 16) | ((uint32_t)t.k1 << 24);
+      ls.off[j] = (int)(reinterpret_cast<uintptr_t>(t.src) >> 2);
+      ls.soff[j] = a_off(t.row0, t.k0) | (a_off(t.row1, t.k1) << 16);
+    }
+  }
+}
+
+// issue the FB loads of (tile m0, k-block kb); `okmask` bit j = slot j holds real data
+__device__ __forceinline__ void load_block(const FrontParams& p, const LaneSlots& ls, const float* __restrict__ src, int m0,
+                                           int kb, float4 (&v)[FB], uint32_t& okmask) {
+  const float* tbase;
+  int limit;                            // rows available from the tile start (raw-IQ: token rows; ViT: rows of whole frames)
+  const bool by_row = p.kind == AMC_KIND_RAWIQ;
+  if (by_row) {
+    tbase = p.raw ? src + (size_t)m0 * p.S * 2 : src;
+    limit = p.M - m0;
+  } else {
+    const int f0 = m0 / p.Ttok;
+    tbase = src + (size_t)f0 * 2048 + (size_t)kb * ls.kb_stride;
+    limit = (p.B - f0) * p.Ttok;
+  }
+  okmask = 0u;
+#pragma unroll
+  for (int j = 0; j < FB; ++j) {
+    const int row0 = ls.meta[j] & 0xFF;
+    const bool ok = ls.off[j] >= 0 && row0 < limit && !(p.dbg & 1);
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      okmask |= 1u << j;
+      const float* a;
+      if (by_row && !p.raw) {           // model layout [B, 2, L]: frame / token of the row (Ttok is a power of two)
+        const int gr = m0 + row0, b = gr >> p.lg_ttok, t = gr & (p.Ttok - 1);
+        const int k0 = (ls.meta[j] >> 16) & 0xFF, c = k0 >= p.S ? 1 : 0;
+        a = src + ((size_t)b * 2 + c) * p.L + (size_t)t * p.S + (k0 - c * p.S);
+      } else {
+        a = tbase + ls.off[j];
+      }
+      v[j] = __ldg(reinterpret_cast<const float4*>(a));
+    }
+  }
+}
+
+// normalise, convert and scatter the loaded values into the swizzled A stage (and stream them to Aout in training)
+__device__ __forceinline__ void store_block(const FrontParams& p, const LaneSlots& ls, uint32_t sa, int m0, int kb,
+                                            const float4 (&v)[FB], uint32_t okmask) {
+  const int kbase = kb * FBK;          // column of this k-block inside the [M, K] operand (Aout)
+#pragma unroll
+  for (int j = 0; j < FB; ++j) {
+    if (ls.off[j] < 0) continue;
+    const bool ok = (okmask >> j) & 1u;
+    const int row0 = ls.meta[j] & 0xFF, row1 = (ls.meta[j] >> 8) & 0xFF, k0 = (ls.meta[j] >> 16) & 0xFF, k1 = ls.meta[j] >> 24;
+    if (p.raw) {
+      uint32_t wi = 0u, wq = 0u;
+      if (ok) {
+        wi = pk((v[j].x - p.mean[0]) * p.inv_std[0], (v[j].z - p.mean[0]) * p.inv_std[0]);
+        wq = pk((v[j].y - p.mean[1]) * p.inv_std[1], (v[j].w - p.mean[1]) * p.inv_std[1]);
+        if (p.Aout) {
+          *reinterpret_cast<uint32_t*>(p.Aout + (size_t)(m0 + row0) * p.K + kbase + k0) = wi;
+          *reinterpret_cast<uint32_t*>(p.Aout + (size_t)(m0 + row1) * p.K + kbase + k1) = wq;
         }
       }
+      sts32(sa + (ls.soff[j] & 0xFFFFu), wi);
+      sts32(sa + (ls.soff[j] >> 16), wq);
+    } else {
+      const uint32_t w0_ = pk(v[j].x, v[j].y), w1_ = pk(v[j].z, v[j].w);
+      if (ok && p.Aout)
+        *reinterpret_cast<uint2*>(p.Aout + (size_t)(m0 + row0) * p.K + kbase + k0) = make_uint2(w0_, w1_);
+      sts64(sa + (ls.soff[j] & 0xFFFFu), w0_, w1_);
     }
   }
 }
@@ -242,13 +307,20 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
   } else if (warp < F_EPI_WARP0) {
     // ===================== converter warps =====================
     const int cw = warp - F_CONV_WARP0;
+    LaneSlots ls;
+    make_lane_slots(p, cw, lane, ls);
     int stage = 0;
     uint32_t phase = 0;
+    // the FB loads of a k-block are issued before waiting for its shared-memory stage, so DRAM latency overlaps the
+    // wait for the tensor core to release the stage
     for (int tm = cta_m; tm < p.tiles_m; tm += m_stride) {
       for (int kb = 0; kb < p.kb_total; ++kb) {
+        float4 cur[FB];
+        uint32_t ok_cur = 0u;
+        load_block(p, ls, src, tm * FBM, kb, cur, ok_cur);
         mbar_wait(empty_bar + stage, phase ^ 1);
-        convert_block(p, src, smem_u32(sA + (size_t)stage * C::A_BYTES), tm * FBM, kb, cw, lane);
-        fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        if (!(p.dbg & 8)) store_block(p, ls, smem_u32(sA + (size_t)stage * C::A_BYTES), tm * FBM, kb, cur, ok_cur);
+        if (!(p.dbg & 32)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar + stage);
         if (++stage == nstage) { stage = 0; phase ^= 1; }
@@ -258,17 +330,28 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
     // ===================== epilogue warps =====================
     const int ew = warp - F_EPI_WARP0;
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                          // which half of the tile's columns this warp drains
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t stg = smem_u32(stage_base + ew * (32 * F_STG_LD));
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    float* const D32 = epi.D32;
+    bf16* const D16 = reinterpret_cast<bf16*>(epi.D16);
     for (int tm = cta_m; tm < p.tiles_m; tm += m_stride) {
       const int m_base = tm * FBM + quad * 32;
+      // output row (CLS-shifted, encoder.py:104-105) and token index of the 8 rows this lane touches in every chunk
+      int orow[8], tok[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = m_base + it * 4 + sub_r;
+        const int b = m / epi.map_Ttok, t = m - b * epi.map_Ttok + epi.map_cls;
+        tok[it] = t;
+        orow[it] = m < p.M ? b * epi.map_T + t : -1;
+      }
       mbar_wait(tfull_bar + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      const int c_begin = half * (BN / 2), c_end = min((half + 1) * (BN / 2), p.d - n0);
+      const int c_begin = 0;
+      const int c_end = (p.dbg & 16) ? 0 : min(BN, p.d - n0);
       uint32_t r[32];
       if (c_begin < c_end) tmem_ld32(taddr + c_begin, r);
 #pragma unroll 1
@@ -279,15 +362,28 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
           sts128(stg + (uint32_t)(lane * F_STG_LD + (((j >> 2) ^ (lane & 7)) << 2)) * 4, r[j], r[j + 1], r[j + 2], r[j + 3]);
         if (c + 32 < c_end) tmem_ld32(taddr + c + 32, r);
         __syncwarp();
-        float4 v[8];
+        const int n = n0 + c + sub_c;
+        if (n < p.d) {                    // d % 8 == 0: a float4 is never ragged
+          const float4 bias = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
+          float4 pe[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub_r;
-          v[it] = lds128(stg + (uint32_t)(rr * F_STG_LD + ((((lane & 7)) ^ (rr & 7)) << 2)) * 4);
+          for (int it = 0; it < 8; ++it) pe[it] = (p.dbg & 4) ? bias : __ldg(reinterpret_cast<const float4*>(epi.pos + (size_t)tok[it] * p.d + n));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub_r;
+            float4 v = lds128(stg + (uint32_t)(rr * F_STG_LD + ((((lane & 7)) ^ (rr & 7)) << 2)) * 4);
+            if (orow[it] < 0) continue;
+            v.x += bias.x + pe[it].x; v.y += bias.y + pe[it].y; v.z += bias.z + pe[it].z; v.w += bias.w + pe[it].w;
+            const size_t o = (size_t)orow[it] * p.d + n;
+            if (epi.drop.p > 0.f) {
+              const float4 k = dropout_mult4(epi.drop, epi.drop_site, (uint64_t)o >> 2);
+              v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+            }
+            if (p.dbg & 2) { if (v.x == 1234.5f) D32[0] = v.y; continue; }
+            if (D32) *reinterpret_cast<float4*>(D32 + o) = v;
+            if (D16) store4(D16 + o, v);
+          }
         }
-#pragma unroll
-        for (int it = 0; it < 8; ++it)
-          epi_apply4<bf16>(epi, m_base + it * 4 + sub_r, n0 + c + sub_c, v[it], p.M, p.d, p.vec_ok != 0);
         __syncwarp();
       }
       tc_fence_before();
@@ -374,20 +470,27 @@ int frontend_fused(const AmcDesc& D, int Ttok, int K, const float* src, const bf
     // one k-block (2S <= 64); 128-token tiles made of whole 64-sample warp-loads; float4 never straddles a token
     if (D.in_ch != 2 || !pow2(S) || S < 4 || 2 * S > 64 || K != 2 * S) return 0;
     if (!p.raw && (Ttok % 1 != 0 || D.seq_len % 4 != 0)) return 0;
+    if (!pow2(Ttok)) return 0;
     p.S = S; p.L = D.seq_len;
+    p.lg_ttok = 0;
+    while ((1 << p.lg_ttok) < Ttok) ++p.lg_ttok;
   } else {
     if (D.in_ch != 1 || D.img_h != 32 || D.img_w != 64 || (D.patch != 4 && D.patch != 8 && D.patch != 16)) return 0;
     if (FBM % Ttok != 0 && Ttok % FBM != 0) return 0;
     p.p = D.patch;
   }
+  p.vec_ok = epi_vec_ok<bf16>(epi, d) ? 1 : 0;
+  if (!p.vec_ok || epi.bias == nullptr || epi.pos == nullptr || epi.D16 == nullptr || epi.ldd16 != d ||
+      (epi.D32 && epi.ldd32 != d))
+    return 0;
   if (probe_only) {
     *handled = true;
     return 0;
   }
   p.mean[0] = D.norm[0]; p.inv_std[0] = 1.f / D.norm[1];
   p.mean[1] = D.norm[2]; p.inv_std[1] = 1.f / D.norm[3];
-  p.vec_ok = epi_vec_ok<bf16>(epi, d) ? 1 : 0;
   p.Aout = Aout;
+  { const char* e = getenv("AMC_FRONT_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (d <= 128) AMC_TRY(launch_front<128>(D, p, epi, src, W, st));
   else AMC_TRY(launch_front<256>(D, p, epi, src, W, st));
   *handled = true;
