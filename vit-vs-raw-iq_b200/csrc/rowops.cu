@@ -540,10 +540,13 @@ __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int 
                                                               const float* __restrict__ s_xhat,
                                                               float* __restrict__ dW, float* __restrict__ dbias,
                                                               float* __restrict__ dlnw, float* __restrict__ dlnb) {
-  constexpr int KG = 24;
+  constexpr int KG = 24, ROWS = 32;
+  __shared__ float sdl[ROWS * 64];                  // this block's rows of dlogits (C <= 64), staged once
   const int c = blockIdx.x * 128 + threadIdx.x;
-  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int per = min((B + gridDim.y - 1) / gridDim.y, ROWS);
   const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  for (int i = threadIdx.x; i < (b1 - b0) * C; i += blockDim.x) sdl[i] = __ldg(dlogits + (size_t)b0 * C + i);
+  __syncthreads();
   if (c < d) {
     for (int k0 = 0; k0 < C; k0 += KG) {
       float acc[KG];
@@ -551,10 +554,10 @@ __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int 
       for (int k = 0; k < KG; ++k) acc[k] = 0.f;
       for (int b = b0; b < b1; ++b) {
         const float h = s_hl[(size_t)b * d + c];
-        const float* dl = dlogits + (size_t)b * C + k0;
+        const float* dl = sdl + (b - b0) * C + k0;
 #pragma unroll
         for (int k = 0; k < KG; ++k)
-          if (k0 + k < C) acc[k] = fmaf(__ldg(dl + k), h, acc[k]);
+          if (k0 + k < C) acc[k] = fmaf(dl[k], h, acc[k]);
       }
 #pragma unroll
       for (int k = 0; k < KG; ++k)
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(128) head_bwd_params_kernel(int B, int d, int 
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < C) {
     float sbias = 0.f;
-    for (int b = b0; b < b1; ++b) sbias += __ldg(dlogits + (size_t)b * C + threadIdx.x);
+    for (int b = b0; b < b1; ++b) sbias += sdl[(b - b0) * C + threadIdx.x];
     atomicAdd(dbias + threadIdx.x, sbias);
   }
 }
@@ -850,9 +853,29 @@ template int cls_rows<bf16>(int, int, int, const float*, const float*, bf16*, fl
 
 int cls_grad(int B, int T, int d, const float* dx0, float* dcls, const DropoutCfg& drop, cudaStream_t st) {
   if (B == 0) return 0;
-  cls_grad_kernel<<<dim3(ceil_div(d, 128), std::min(B, 64)), 128, 0, st>>>(B, T, d, dx0, dcls, drop);
+  cls_grad_kernel<<<dim3(ceil_div(d, 128), std::max(1, std::min(B / 8, 148 * 4))), 128, 0, st>>>(B, T, d, dx0, dcls, drop);
   AMC_LAUNCH_CHECK();
   return 0;
+}
+
+// vector version (d % 4 == 0, 16-byte aligned): one float4 per thread, row arithmetic once per float4
+template <typename E>
+__global__ void __launch_bounds__(256) gather_tok_rows_vec_kernel(int B, int T, int Ttok, int d4, int has_cls,
+                                                                  const float4* __restrict__ dx0, E* __restrict__ out,
+                                                                  DropoutCfg drop) {
+  const size_t total = (size_t)B * Ttok * d4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % d4);
+    const size_t row = i / d4;
+    const int t = (int)(row % Ttok), b = (int)(row / Ttok);
+    const size_t o4 = ((size_t)b * T + has_cls + t) * d4 + c4;
+    float4 v = __ldg(dx0 + o4);
+    if (drop.p > 0.f) {
+      const float4 k = dropout_mult4(drop, site_pe(), (uint64_t)o4);
+      v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+    }
+    store4(out + i * 4, v);
+  }
 }
 
 template <typename E>
@@ -860,6 +883,13 @@ int gather_tok_rows(int B, int T, int Ttok, int d, int has_cls, const float* dx0
                     cudaStream_t st) {
   const size_t total = (size_t)B * Ttok * d;
   if (total == 0) return 0;
+  if (d % 4 == 0 && (reinterpret_cast<uintptr_t>(dx0) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int blocks = (int)std::min<size_t>((total / 4 + 255) / 256, 148 * 16);
+    gather_tok_rows_vec_kernel<E><<<blocks, 256, 0, st>>>(B, T, Ttok, d / 4, has_cls, reinterpret_cast<const float4*>(dx0),
+                                                          out, drop);
+    AMC_LAUNCH_CHECK();
+    return 0;
+  }
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   gather_tok_rows_kernel<E><<<blocks, 256, 0, st>>>(B, T, Ttok, d, has_cls, dx0, out, drop);
   AMC_LAUNCH_CHECK();
@@ -886,7 +916,7 @@ int head_bwd(int B, int T, int d, int C, int has_cls, int head_ln, const float* 
   head_bwd_rows_kernel<<<ceil_div(B, 4), 128, 0, st>>>(B, T, d, C, has_cls, head_ln, dlogits, W, lnw, s_xhat,
                                                        s_rstd, dxL, dhl_scratch);
   AMC_LAUNCH_CHECK();
-  const int chunks = std::max(1, std::min(ceil_div(B, 64), 148));
+  const int chunks = ceil_div(B, 32);       // 32 rows per block (the kernel's shared-memory staging size)
   head_bwd_params_kernel<<<dim3(ceil_div(d, 128), chunks), 128, 0, st>>>(B, d, C, head_ln, dlogits, s_hl, dhl_scratch, s_xhat,
                                                               dW, dbias, dlnw, dlnb);
   AMC_LAUNCH_CHECK();
