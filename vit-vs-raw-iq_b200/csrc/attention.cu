@@ -600,15 +600,22 @@ __global__ void __launch_bounds__(256) attn_mma_fwd_kernel(int B, int T, int h, 
   __syncthreads();
   const int stride_f = gridDim.x * F;
   int f0 = blockIdx.x * F;
-  if (tid == 0 && f0 < B) bulk_rows_in(blk0, s_in, qkv + (size_t)f0 * T * ld, min(F, B - f0) * T, ld, bars);
+  // Row copies are dealt round-robin to lane 0 of every warp: issued by one thread, the ~60 bulk copies of an
+  // iteration cost about a quarter of it.  Thread 0 arms the barrier with the byte count, the copies may land first.
+  auto rows_in = [&](bf16* dst, int fs, uint64_t* bar) {      // called by lane 0 of each warp
+    const int rows = min(F, B - fs) * T;
+    if (warp == 0) mbar_expect(bar, (uint32_t)(rows * ld * 2));
+    for (int r = warp; r < rows; r += nw)
+      bulk_g2s(dst + (size_t)r * s_in, qkv + ((size_t)fs * T + r) * ld, (uint32_t)(ld * 2), bar);
+  };
+  if (lane == 0 && f0 < B) rows_in(blk0, f0, bars);
   for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
     const int nf = min(F, B - f0);
     bf16* blk = blk0 + (it & 1) * in_elems;
-    if (tid == 0) {
+    if (lane == 0) {
       const int fn = f0 + stride_f;
-      if (fn < B) bulk_rows_in(blk0 + ((it + 1) & 1) * in_elems, s_in, qkv + (size_t)fn * T * ld, min(F, B - fn) * T, ld,
-                               bars + ((it + 1) & 1));
-      bulk_wait_read0();                       // previous iteration's output rows have left oblk
+      if (fn < B) rows_in(blk0 + ((it + 1) & 1) * in_elems, fn, bars + ((it + 1) & 1));
+      bulk_wait_read0();                       // this warp's output rows of the previous iteration have left oblk
     }
     mbar_wait_parity(bars + (it & 1), (it >> 1) & 1);
     __syncthreads();
@@ -646,9 +653,13 @@ __global__ void __launch_bounds__(256) attn_mma_fwd_kernel(int B, int T, int h, 
     }
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) bulk_rows_out(out + (size_t)f0 * T * d, oblk, s_out, nf * T, d);
+    if (lane == 0) {
+      for (int r = warp; r < nf * T; r += nw)
+        bulk_s2g(out + ((size_t)f0 * T + r) * d, oblk + (size_t)r * s_out, (uint32_t)(d * 2));
+      bulk_commit_group();
+    }
   }
-  if (tid == 0) bulk_wait_all0();
+  if (lane == 0) bulk_wait_all0();
 }
 
 template <int KD>
@@ -673,22 +684,23 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, 
   __syncthreads();
   const int stride_f = gridDim.x * F;
   int f0 = blockIdx.x * F;
-  auto issue = [&](int fs) {
+  // row copies dealt round-robin to lane 0 of every warp (see the forward kernel); thread 0 arms the barrier
+  auto issue = [&](int fs) {                                  // called by lane 0 of each warp
     const int rows = min(F, B - fs) * T;
-    mbar_expect(bar, (uint32_t)(rows * (ld + d) * 2));
-    for (int r = 0; r < rows; ++r) {
+    if (warp == 0) mbar_expect(bar, (uint32_t)(rows * (ld + d) * 2));
+    for (int r = warp; r < rows; r += nw) {
       bulk_g2s(blk + (size_t)r * s_in, qkv + ((size_t)fs * T + r) * ld, (uint32_t)(ld * 2), bar);
       bulk_g2s(doblk + (size_t)r * s_do, dout + ((size_t)fs * T + r) * d, (uint32_t)(d * 2), bar);
     }
   };
-  if (tid == 0 && f0 < B) issue(f0);
+  if (lane == 0 && f0 < B) issue(f0);
   // bias gradient of the QKV projection (Appendix B: db = sum of dQ|dK|dV rows): each thread owns up to two
   // 4-column groups of the staged gradient rows and keeps their sums in registers across all its frames
   float4 bsum[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
   const int ngroups = ld >> 2;
   for (uint32_t it = 0; f0 < B; f0 += stride_f, ++it) {
     const int nf = min(F, B - f0);
-    if (tid == 0) bulk_wait_read0();          // previous iteration's gradient rows have left oblk
+    if (lane == 0) bulk_wait_read0();         // this warp's gradient rows of the previous iteration have left oblk
     mbar_wait_parity(bar, it & 1);
     __syncthreads();
     const int g = lane >> 2, cb = (lane & 3) * 2;
@@ -785,8 +797,10 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, 
     }
     fence_async_smem();
     __syncthreads();                          // all reads of q/k/v/dO done, all gradient rows staged
-    if (tid == 0) {
-      bulk_rows_out(dqkv + (size_t)f0 * T * ld, oblk, s_in, nf * T, ld);
+    if (lane == 0) {
+      for (int r = warp; r < nf * T; r += nw)
+        bulk_s2g(dqkv + ((size_t)f0 * T + r) * ld, oblk + (size_t)r * s_in, (uint32_t)(ld * 2));
+      bulk_commit_group();
       const int fn = f0 + stride_f;
       if (fn < B) issue(fn);
     }
@@ -814,7 +828,7 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(int B, int T, int h, 
       }
     }
   }
-  if (tid == 0) bulk_wait_all0();
+  if (lane == 0) bulk_wait_all0();
 }
 
 inline bool use_mma(int T, int h, int dh) {
