@@ -4,6 +4,8 @@
 // reference materialises [B,h,T,T] fp32: scale_dot_product_attention.py:26-37).
 // Backward recomputes P from Q,K (SURVEY Appendix B "what to save"): phase 1 is query-row parallel
 // (row statistics, dQ), phase 2 is key-row parallel (dK, dV) -- no atomics, deterministic.
+#include <cstdlib>
+
 #include "attention.cuh"
 #include "rowops.cuh"
 
@@ -843,10 +845,13 @@ inline size_t mma_bwd_bytes(int T, int h, int dh, int F) {
   return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2 + 8 * 2 * 16 * 24 * 2;
 }
 inline int mma_frames(int T, int h, int dh, bool bwd) {
+  if (const char* e = getenv("AMC_ATTN_F")) return std::max(1, atoi(e));
   int F = std::max(1, ceil_div(16, h));                 // at least ~2 pairs per warp
   while (F < 8 && (bwd ? mma_bwd_bytes(T, h, dh, F + 1) : mma_fwd_bytes(T, h, dh, F + 1)) <= 100 * 1024) ++F;
   return F;
 }
+// resident CTAs per SM for a given dynamic shared-memory size (256 threads each)
+inline int mma_ctas_per_sm(size_t sm) { return (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (sm + 1024))); }
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core attention for 16 < T <= 288 tokens (bf16, head dim 16*KD): the general single-CTA kernel.
@@ -1293,7 +1298,7 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse,
     if (use_mma(T, h, dh)) {
       const int F = mma_frames(T, h, dh, false);
       const size_t sm = mma_fwd_bytes(T, h, dh, F);
-      const int grid = std::min(ceil_div(B, F), 148 * 2);
+      const int grid = std::min(ceil_div(B, F), 148 * mma_ctas_per_sm(sm));
       const float sc = 1.f / sqrtf((float)dh);
 #define AMC_LAUNCH_MMA_FWD(KD)                                                                                      \
   do {                                                                                                              \
@@ -1386,7 +1391,7 @@ int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* out, 
     if (use_mma(T, h, dh)) {
       const int F = mma_frames(T, h, dh, true);
       const size_t sm = mma_bwd_bytes(T, h, dh, F);
-      const int grid = std::min(ceil_div(B, F), 148 * 2);
+      const int grid = std::min(ceil_div(B, F), 148 * mma_ctas_per_sm(sm));
       const float sc = 1.f / sqrtf((float)dh);
 #define AMC_LAUNCH_MMA_BWD(KD)                                                                                      \
   do {                                                                                                              \
