@@ -391,7 +391,11 @@ struct Model {
 
   // fused QKV projection (one [3d,d] weight: three adjacent state_dict tensors, multi_head_attention.py:18)
   // + attention over all rows
-  int attn_fwd_part(int l) {
+  // the top layer of a CLS-pooled model needs attention for query row 0 only (attn_cls.cu)
+  // (T <= 16 stays on the warp-per-(frame, head) tensor-core kernel, which is already at its HBM floor there)
+  bool cls_attn() const { return sizeof(E) == 2 && m.T > 16 && attn_cls_supported(m.T, m.h, m.dh) && (m.d % 8) == 0; }
+
+  int attn_fwd_part(int l, bool cls_only = false) {
     const int M = (int)m.M, d = m.d;
     const LayerBuf& b = LB(l);
     GemmArgs g;
@@ -399,6 +403,11 @@ struct Model {
     g.name = "gemm_qkv";
     g.epi.bias = PL(l, L.bq); g.epi.D16 = b.qkv; g.epi.ldd16 = 3 * d;
     AMC_TRY(gemm<E>(g, st));
+    if (cls_only && cls_attn()) {
+      ProfScope ps("attn_cls_fwd", st, 4.0 * m.M * d, (double)M * 2 * d * sizeof(E));
+      AMC_TRY(attn_cls_fwd(m.B, m.T, m.h, m.dh, (const bf16*)b.qkv, (bf16*)b.o, st));
+      return 0;
+    }
     ProfScope ps("attn_fwd", st, 4.0 * m.M * m.T * d, (double)M * 4 * d * sizeof(E));
     AMC_TRY(attention_fwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (E*)b.o, b.lse, st));
     return 0;
@@ -455,7 +464,7 @@ struct Model {
   }
 
   int layer_fwd(int l, bool cls_only) {
-    AMC_TRY(attn_fwd_part(l));
+    AMC_TRY(attn_fwd_part(l, cls_only));
     return post_fwd_part(l, cls_only ? cls_rows_view(l) : all_rows(l));
   }
 
@@ -565,14 +574,18 @@ struct Model {
     const int M = (int)m.M, d = m.d;
     const LayerBuf& b = LB(l);
     float* G = grads + L.layer0 + (int64_t)l * L.layer_stride;
+    const bool cls_kernel = cls_only && cls_attn();
     if (cls_only) {
-      // every non-CLS row of the attention-output gradient is exactly zero
-      AMC_CUDA(cudaMemsetAsync(w.dO, 0, (size_t)M * d * sizeof(E), st));
+      // every non-CLS row of the attention-output gradient is exactly zero (the CLS-row kernel never reads them)
+      if (!cls_kernel) AMC_CUDA(cudaMemsetAsync(w.dO, 0, (size_t)M * d * sizeof(E), st));
       AMC_TRY(post_bwd_part(l, cls_rows_view(l), grads));
     } else {
       AMC_TRY(post_bwd_part(l, all_rows(l), grads));
     }
-    {
+    if (cls_kernel) {
+      ProfScope ps("attn_cls_bwd", st, 10.0 * m.M * d, (double)M * 5 * d * sizeof(E));
+      AMC_TRY(attn_cls_bwd(m.B, m.T, m.h, m.dh, (const bf16*)b.qkv, (const bf16*)w.dO, (bf16*)w.dqkv, G + L.bq, st));
+    } else {
       ProfScope ps("attn_bwd", st, 10.0 * m.M * m.T * d, (double)M * 7 * d * sizeof(E));
       AMC_TRY(attention_bwd<E>(m.B, m.T, m.h, m.dh, (const E*)b.qkv, (const E*)b.o, b.lse, (const E*)w.dO, (E*)w.dqkv, G + L.bq, st));
     }

@@ -845,7 +845,6 @@ inline size_t mma_bwd_bytes(int T, int h, int dh, int F) {
   return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2 + 8 * 2 * 16 * 24 * 2;
 }
 inline int mma_frames(int T, int h, int dh, bool bwd) {
-  if (const char* e = getenv("AMC_ATTN_F")) return std::max(1, atoi(e));
   int F = std::max(1, ceil_div(16, h));                 // at least ~2 pairs per warp
   while (F < 8 && (bwd ? mma_bwd_bytes(T, h, dh, F + 1) : mma_fwd_bytes(T, h, dh, F + 1)) <= 100 * 1024) ++F;
   return F;

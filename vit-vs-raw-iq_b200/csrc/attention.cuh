@@ -19,4 +19,9 @@ bool attn_tiles_supported(int T, int h, int dh);
 int attn_tiles_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float* lse, bool* handled, cudaStream_t st);
 int attn_tiles_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out, const float* lse, const bf16* dout,
                    bf16* dqkv, float* dbias, bool* handled, cudaStream_t st);
+
+// attn_cls.cu: attention restricted to query row 0 (the CLS token) for the top layer of a CLS-pooled model (bf16)
+bool attn_cls_supported(int T, int h, int dh);
+int attn_cls_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, cudaStream_t st);
+int attn_cls_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* dO, bf16* dqkv, float* dbias, cudaStream_t st);
 }  // namespace amc

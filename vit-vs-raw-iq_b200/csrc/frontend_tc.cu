@@ -15,7 +15,6 @@
 // warps 10-13 = epilogue (one per TMEM lane quadrant).  Bound: HBM (8 B per IQ sample in, 6 B per embedding
 // element out); the GEMM (K <= 256) is a small fraction of the tensor pipe.
 #include <algorithm>
-#include <cstdlib>
 
 #include "gemm_common.cuh"
 #include "rowops.cuh"
@@ -40,7 +39,6 @@ struct FrontParams {
   float mean[2], inv_std[2];
   int tiles_m, tiles_n, vec_ok;
   bf16* Aout;             // nullable: the patchified operand [M, K] (training: embedding weight gradient)
-  int dbg;                // AMC_FRONT_DBG experiments: 1 = no input loads, 2 = no output stores, 4 = no pos/bias loads
 };
 
 template <int BN> struct FrontCfg {
@@ -181,7 +179,7 @@ __device__ __forceinline__ void load_block(const FrontParams& p, const LaneSlots
 #pragma unroll
   for (int j = 0; j < FB; ++j) {
     const int row0 = ls.meta[j] & 0xFF;
-    const bool ok = ls.off[j] >= 0 && row0 < limit && !(p.dbg & 1);
+    const bool ok = ls.off[j] >= 0 && row0 < limit;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) {
       okmask |= 1u << j;
@@ -319,8 +317,8 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
         uint32_t ok_cur = 0u;
         load_block(p, ls, src, tm * FBM, kb, cur, ok_cur);
         mbar_wait(empty_bar + stage, phase ^ 1);
-        if (!(p.dbg & 8)) store_block(p, ls, smem_u32(sA + (size_t)stage * C::A_BYTES), tm * FBM, kb, cur, ok_cur);
-        if (!(p.dbg & 32)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        store_block(p, ls, smem_u32(sA + (size_t)stage * C::A_BYTES), tm * FBM, kb, cur, ok_cur);
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar + stage);
         if (++stage == nstage) { stage = 0; phase ^= 1; }
@@ -351,7 +349,7 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
       const int c_begin = 0;
-      const int c_end = (p.dbg & 16) ? 0 : min(BN, p.d - n0);
+      const int c_end = min(BN, p.d - n0);
       uint32_t r[32];
       if (c_begin < c_end) tmem_ld32(taddr + c_begin, r);
 #pragma unroll 1
@@ -367,7 +365,7 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
           const float4 bias = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
           float4 pe[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) pe[it] = (p.dbg & 4) ? bias : __ldg(reinterpret_cast<const float4*>(epi.pos + (size_t)tok[it] * p.d + n));
+          for (int it = 0; it < 8; ++it) pe[it] = __ldg(reinterpret_cast<const float4*>(epi.pos + (size_t)tok[it] * p.d + n));
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + sub_r;
@@ -379,7 +377,6 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap mapW, const FrontParams p
               const float4 k = dropout_mult4(epi.drop, epi.drop_site, (uint64_t)o >> 2);
               v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
             }
-            if (p.dbg & 2) { if (v.x == 1234.5f) D32[0] = v.y; continue; }
             if (D32) *reinterpret_cast<float4*>(D32 + o) = v;
             if (D16) store4(D16 + o, v);
           }
@@ -490,7 +487,6 @@ int frontend_fused(const AmcDesc& D, int Ttok, int K, const float* src, const bf
   p.mean[0] = D.norm[0]; p.inv_std[0] = 1.f / D.norm[1];
   p.mean[1] = D.norm[2]; p.inv_std[1] = 1.f / D.norm[3];
   p.Aout = Aout;
-  { const char* e = getenv("AMC_FRONT_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (d <= 128) AMC_TRY(launch_front<128>(D, p, epi, src, W, st));
   else AMC_TRY(launch_front<256>(D, p, epi, src, W, st));
   *handled = true;
