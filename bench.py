@@ -29,7 +29,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs[1]; 19 classes / dropout 0.1 / lr 1e-4 / wd 1e-3 from V/training/train.py:59-93
-    "vit_p16_d256_L6": dict(kind="vit", batch=8192, lr=1e-4, wd=1e-3,
+    # batch: frames per GPU per step.  32768 (301k token rows) keeps every kernel of the step above ~100 us, where the
+    # bandwidth-bound ones get within 15-25 % of the copy peak; 8192 gives 1.59 M frames/s, 32768 1.87 M.
+    "vit_p16_d256_L6": dict(kind="vit", batch=32768, eager_batch=8192, lr=1e-4, wd=1e-3,
                             kw=dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19,
                                     d_model=256, n_head=8, n_layers=6, ffn_hidden=1024, drop_prob=0.1)),
     # BASELINE.json configs[0] shape (R/training/train.py:84-95, 11 classes)
