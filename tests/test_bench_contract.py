@@ -27,3 +27,26 @@ def test_reference_arm_other_ranks_exit_silently():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_algorithmic_flops_match_the_survey_table():
+    """forward GFLOP per frame of the BASELINE configs (the numerators of every roofline figure)."""
+    import bench
+    expect = {"rawiq_seg16_d128_L6": 0.2691, "vit_p16_d256_L6": 0.0865, "vit_p4_d128_L6": 0.3560,
+              "rawiq_sps1_seg8_d256_L6": 1.3207, "rawiq_sps2_seg8_d256_L6": 2.8333}
+    for name, gf in expect.items():
+        got = bench.flops_per_frame(bench.WORKLOADS[name]) / 1e9
+        assert abs(got - gf) / gf < 5e-3, (name, got, gf)
+
+
+def test_ncu_launch_list_summary_parses_the_committed_capture(tmp_path):
+    """tools/ncu_summary.py turns the ncu CSV launch list into the per-kernel share table under profiles/."""
+    src = os.path.join(ROOT, "profiles", "r1_launches_train.csv")
+    out = tmp_path / "launches.md"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "launches", src, str(out)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    text = out.read_text()
+    assert "gemm_tc_kernel<256, 1, 0>" in text and "frontend_tc_kernel<256>" in text
+    shares = [float(l.split("|")[-2].strip().rstrip("%")) for l in text.splitlines() if l.startswith("| `")]
+    assert abs(sum(shares) - 100.0) < 1.0

@@ -26,8 +26,12 @@ from oracle import amc_oracle as O          # measurement script: the port is th
 from oracle import amc_torch_port as TP
 
 
+LR0 = float(os.environ.get("LR", "1e-3"))
+ARMS = os.environ.get("ARMS", "ref,fp32,bf16").split(",")
+
+
 def lr_at(it):
-    return 1e-3 * 0.5 ** (it // max(1, STEPS // 4))        # stand-in for ReduceLROnPlateau(factor 0.5)
+    return LR0 * 0.5 ** (it // max(1, STEPS // 4))         # stand-in for ReduceLROnPlateau(factor 0.5)
 
 
 def run_ref(seed, model_kind, state_dict):
@@ -43,7 +47,7 @@ def run_ref(seed, model_kind, state_dict):
             v.requires_grad_(True)
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(5000 + seed)
-    ts = TP.TrainStep(p, cfg, drop_prob=0.1, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.99), max_norm=1.0, label_smoothing=0.1)
+    ts = TP.TrainStep(p, cfg, drop_prob=0.1, lr=LR0, weight_decay=1e-4, betas=(0.9, 0.99), max_norm=1.0, label_smoothing=0.1)
     st = torch.tensor([stats["i_mean"], stats["q_mean"]], device=dev), torch.tensor([stats["i_std"], stats["q_std"]], device=dev)
 
     def frame(x):                                    # dataset.py:215-224 on the device
@@ -77,7 +81,7 @@ def run(seed, dtype, model_kind, want_state=False):
     if want_state:
         return {k: v.detach().clone() for k, v in m.state_dict().items()}
     m.set_raw_input(stats)
-    ts = TrainStep(m, lr=1e-3, weight_decay=1e-4)
+    ts = TrainStep(m, lr=LR0, weight_decay=1e-4)
     order = torch.from_numpy(np.random.default_rng(seed).permutation(NTRAIN)).to(dev)
     for it in range(STEPS):
         ts.lr = lr_at(it)
@@ -93,11 +97,14 @@ out = {}
 for kind in ("rawiq", "vit"):
     res = {"ref": [], "fp32": [], "bf16": []}
     for seed in range(int(os.environ.get("SEEDS", "5"))):
-        for dt in ("ref", "fp32", "bf16"):
+        for dt in ARMS:
             t = time.time()
             acc = run_ref(seed, kind, run(seed, "fp32", kind, want_state=True)) if dt == "ref" else run(seed, dt, kind)
             res[dt].append(acc)
             print(f"{kind} seed {seed} {dt}: {acc:.2f}%  ({time.time()-t:.0f}s)", flush=True)
+    for k in res:
+        if not res[k]:
+            res[k] = [float("nan")] * max(len(v) for v in res.values())
     r, f, b = np.array(res["ref"]), np.array(res["fp32"]), np.array(res["bf16"])
     sd = lambda a: float(a.std(ddof=1)) if len(a) > 1 else None
     out[kind] = {"ref": res["ref"], "fp32": res["fp32"], "bf16": res["bf16"],
@@ -105,5 +112,6 @@ for kind in ("rawiq", "vit"):
                  "fp32_minus_ref_pt": float(f.mean() - r.mean()), "bf16_minus_ref_pt": float(b.mean() - r.mean()),
                  "seed_std": {"ref": sd(r), "fp32": sd(f), "bf16": sd(b)},
                  "std_err_of_mean_diff_bf16_ref": float(np.sqrt((sd(r) ** 2 + sd(b) ** 2) / len(r))) if len(r) > 1 else None,
+                 "paired_bf16_minus_ref": (b - r).tolist(), "lr0": LR0,
                  "steps": STEPS, "batch": B, "test_frames": NTEST, "chance_pct": 100.0 / 11}
 print(json.dumps(out))
