@@ -12,10 +12,11 @@
 // Math is mma.sync m16n8k16 (bf16 in, fp32 accumulate): with dh = 16..64 the tensor pipe is not the limiter --
 // the exp / scale / pack work per score element is ("issue/SMEM-bound in practice at dh=16") -- so
 // the kernels minimise instructions per score element rather than chase tcgen05:
-//   forward : a warp owns 16 query rows; scores of up to 144 keys stay in accumulator registers (one chunk),
-//             longer rows take a second chunk with an online rescale; exp2 with the 1/sqrt(dh)*log2(e) factor
+//   forward : a warp owns 16 query rows and walks the keys in chunks of 48 (or 80) with an online-softmax rescale, so
+//             the score fragment stays small enough for two CTAs per SM; exp2 with the 1/sqrt(dh)*log2(e) factor
 //             folded into one FFMA; normalisation is applied to O (dh columns), not to P (T columns);
-//             log2-domain row statistics lse2 = max*c + log2(sum) are saved for the backward.
+//             log2-domain row statistics lse2 = max*c + log2(sum) are saved for the backward; the inputs arrive
+//             through an n-stage TMA ring, the output leaves through double-buffered staging tiles.
 //   backward: a warp owns 16 KEY rows and walks the query blocks: S^T = K Q^T and dP^T = V dO^T come out
 //             transposed, P^T = exp2(S^T c - lse2) needs no row reduction, delta = rowsum(dO * O) is computed once
 //             from the staged tiles.  dV += P^T dO and dK += dS^T Q accumulate in registers; dQ += dS K uses
