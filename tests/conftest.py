@@ -42,6 +42,12 @@ GOLDEN_CASES = {
                            n_head=4, n_layers=2, ffn_hidden=64)),
     "vit_p16": ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19, d_model=64,
                             n_head=8, n_layers=2, ffn_hidden=128)),
+    "vit_p8": ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=8, num_classes=19, d_model=64,
+                           n_head=4, n_layers=2, ffn_hidden=128)),
+    "rawiq_seg32_dh32": ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=4, n_layers=1,
+                                       ffn_hidden=128, use_cls_token=True, embedding_type="segment", segment_size=32)),
+    "rawiq_sps2_seg8": ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=32, n_head=2, n_layers=1,
+                                      ffn_hidden=64, use_cls_token=True, embedding_type="segment", segment_size=8)),
 }
 GOLDEN_HP = dict(lr=1e-3, weight_decay=1e-2, betas=(0.9, 0.99), clip=1.0, label_smoothing=0.1)
 

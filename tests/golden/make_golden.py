@@ -50,6 +50,16 @@ CASES = {
                            n_head=4, n_layers=2, ffn_hidden=64, drop_prob=0.0, device="cpu"), 3),
     "vit_p16": ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=19, d_model=64,
                             n_head=8, n_layers=2, ffn_hidden=128, drop_prob=0.0, device="cpu"), 4),
+    # the tiled single-CTA attention regime: T = 33 (ViT patch 8; raw-IQ segment 32, head dim 32) and the SPS-2
+    # frame of BASELINE configs[2] (L = 2048, segment 8 -> T = 257, two TMA boxes per tile)
+    "vit_p8": ("vit", dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=8, num_classes=19, d_model=64,
+                           n_head=4, n_layers=2, ffn_hidden=128, drop_prob=0.0, device="cpu"), 3),
+    "rawiq_seg32_dh32": ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=4, n_layers=1,
+                                       ffn_hidden=128, drop_prob=0.0, device="cpu", use_cls_token=True,
+                                       embedding_type="segment", segment_size=32), 3),
+    "rawiq_sps2_seg8": ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=32, n_head=2, n_layers=1,
+                                      ffn_hidden=64, drop_prob=0.0, device="cpu", use_cls_token=True,
+                                      embedding_type="segment", segment_size=8), 2),
 }
 
 LR, WD, BETAS, CLIP, LS = 1e-3, 1e-2, (0.9, 0.99), 1.0, 0.1
@@ -179,6 +189,11 @@ def trajectory_case():
     np.savez_compressed(os.path.join(HERE, "trajectory_rawiq.npz"), **out)
     print("trajectory: loss %.4f -> %.4f, acc %.2f -> %.2f" % (losses[0], losses[-1], accs[0], accs[-1]))
 
+
+if __name__ == "__main__" and len(sys.argv) > 1:      # python make_golden.py case [case ...]: only those cases
+    for name in sys.argv[1:]:
+        run_case(name, *CASES[name])
+    sys.exit(0)
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
