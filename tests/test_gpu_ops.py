@@ -96,7 +96,8 @@ def test_gemm_wgrad_split_k(dt, M, N, K):
                                       (2, 33, 2, 128), (37, 9, 8, 32), (6, 17, 8, 16), (3, 32, 4, 32), (9, 9, 4, 8),
                                       (2, 16, 2, 24), (1, 1, 2, 16), (4, 16, 4, 16), (5, 13, 2, 64), (3, 9, 4, 16),
                                       (50, 9, 8, 32), (7, 5, 8, 32), (3, 65, 8, 16), (2, 129, 8, 16), (2, 129, 8, 32),
-                                      (2, 100, 4, 64), (4, 33, 8, 32), (1, 288, 2, 16), (3, 48, 4, 32), (2, 257, 16, 16)])
+                                      (2, 100, 4, 64), (4, 33, 8, 32), (1, 288, 2, 16), (3, 48, 4, 32), (2, 257, 16, 16),
+                                      (1, 257, 2, 64), (2, 200, 1, 64), (3, 144, 2, 32), (2, 64, 4, 16)])
 @pytest.mark.parametrize("saved", [True, False])
 @pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
 def test_attention_fwd_bwd(dt, B, T, h, dh, saved):
@@ -112,6 +113,13 @@ def test_attention_fwd_bwd(dt, B, T, h, dh, saved):
     dbias = torch.zeros(3 * d, device=DEV)
     _lib.check(_lib.lib.amc_attention_fwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr(),
                                           lse.data_ptr() if saved else None, stream()))
+    if dt == _lib.F32 and T * dh * 16 > 227 * 1024:
+        # the fp32 single-CTA backward keeps four [T, dh] fp32 tiles in shared memory: T=257 with dh=64 is outside the
+        # envelope and must fail loudly (no fallback), like every unsupported shape
+        with pytest.raises(RuntimeError, match="unsupported shape"):
+            _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), None, None, dout.data_ptr(),
+                                                  dqkv.data_ptr(), None, stream()))
+        return
     _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr() if saved else None,
                                           lse.data_ptr() if saved else None, dout.data_ptr(), dqkv.data_ptr(),
                                           dbias.data_ptr() if saved else None, stream()))
