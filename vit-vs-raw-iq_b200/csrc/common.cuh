@@ -103,23 +103,25 @@ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool tra
   return c;
 }
 // One counter hash per group of 4 elements: an affine function of the group index (seed, step offset and site folded
-// into the additive key) goes through a murmur3-style finaliser (h), and a second word is derived from the first by one
+// into the additive key) goes through the murmur3 finaliser (h), and a second word is derived from the first by one
 // more multiply + xorshift (b).  The four 16-bit halves of (h, b) are compared with the 16-bit threshold directly on
-// the words (high half: h >= t << 16, low half: (h << 16) >= t << 16).  ~5 integer instructions per element including
+// the words (high half: h >= t << 16, low half: (h << 16) >= t << 16).  ~6 integer instructions per element including
 // the selects -- the dropout mask is ~half of the bias/ReLU/dropout GEMM epilogue's instructions, and those epilogues,
 // not the tensor pipe, bound the K = 256 GEMMs.  Statistics (4M groups, p in {0.1, 0.2, 0.5}): drop rate of every
-// field within 3e-4 of p, |correlation| between fields, neighbouring groups and rows < 4e-3.
+// field within 3e-4 of p; |correlation| between fields, neighbouring groups, rows, seeds, steps and sites < 2e-3.
 // Dropout only needs an unbiased, well-mixed keep decision per element; it is not a cryptographic stream.
 // keep-multipliers (0 or scale) for elements [4*q4, 4*q4+4) of dropout site `site`
 __device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint32_t site, uint64_t q4) {
   const uint32_t key = c.seed_lo ^ (c.off_lo * 0x9E3779B9u) ^ (site * 0x85EBCA6Bu) ^ (c.seed_hi * 0x27D4EB2Fu) ^
                        (c.off_hi * 0x165667B1u);                                        // loop-invariant
   uint32_t h = (uint32_t)q4 * 0x9E3779B1u + ((uint32_t)(q4 >> 32) * 0x7FEB352Du + key);
+  h ^= h >> 16;                                   // murmur3 finaliser: keys that differ in one bit (seed, step, site)
+  h *= 0x85EBCA6Bu;                               // must give uncorrelated masks -- a single multiply left 10 %
+  h ^= h >> 13;                                   // correlation between neighbouring seeds
+  h *= 0xC2B2AE35u;
   h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  uint32_t b = h * 0xC2B2AE35u;
-  b ^= b >> 16;
+  uint32_t b = h * 0x27D4EB2Fu;                   // second word derived from the first
+  b ^= b >> 15;
   const uint32_t t = c.thresh & 0xFFFF0000u;      // keep iff the 16-bit field >= thresh >> 16
   return make_float4((h << 16) >= t ? c.scale : 0.f, h >= t ? c.scale : 0.f, (b << 16) >= t ? c.scale : 0.f,
                      b >= t ? c.scale : 0.f);
