@@ -1,8 +1,9 @@
 """PyTorch-eager restatement of the reference's encoder path (same ATen op sequence as the reference).
 
-TEST / MEASUREMENT INFRASTRUCTURE ONLY (same rules as ``oracle/amc_oracle.py``): imported by ``tests/``,
-by ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs and by ``tools/`` measurement scripts that
-time "the reference's way of doing it" beside the product.  The product never imports it.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY (same rules as ``oracle/amc_oracle.py``): imported by ``tests/``
+(including the accuracy-parity experiment under ``tests/experiments/``) and by ``bench.py``'s
+``cpu_baseline`` / ``gpu_eager_port`` / ``--impl reference`` legs, which time "the reference's way of doing it"
+beside the product.  The product never imports it.
 
 Why it exists next to the numpy oracle: the reference is Python + torch and cannot travel to the GPU box
 (``/root/reference`` does not exist there, and its sources may not be copied).  This file issues the SAME

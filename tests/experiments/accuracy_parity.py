@@ -6,7 +6,7 @@ initial weights (state_dict copied), data order, hyper-parameters and LR schedul
 Dropout masks necessarily differ between `ref` (torch RNG) and ours (counter hash); the seed-to-seed spread of each
 arm is reported beside the mean difference.  Prints a JSON summary."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import vit_vs_raw_iq_b200 as amc
 from vit_vs_raw_iq_b200 import synth
