@@ -190,6 +190,50 @@ def trajectory_case():
     print("trajectory: loss %.4f -> %.4f, acc %.2f -> %.2f" % (losses[0], losses[-1], accs[0], accs[-1]))
 
 
+def trajectory_vit_case():
+    """The same 30-step protocol for the ViT family of the headline benchmark (patch 16 -> T = 9): the reference
+    loop of V/training/train.py:175-220 on a fixed synthetic image set, dropout 0."""
+    AMC = import_reference("vit")
+    kw = dict(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=4, d_model=64, n_head=8,
+              n_layers=2, ffn_hidden=128, drop_prob=0.0, device="cpu")
+    torch.manual_seed(6)
+    model = AMC(**kw)
+    g = torch.Generator().manual_seed(12)
+    N, B = 256, 32
+    y = torch.randint(0, 4, (N,), generator=g)
+    base = torch.randn(4, 1, 32, 64, generator=g)
+    X = base[y] * 0.8 + 0.6 * torch.randn(N, 1, 32, 64, generator=g)
+    out = {"X": X.numpy(), "y": y.numpy()}
+    for k, v in model.state_dict().items():
+        out["param/" + k] = v.detach().numpy().copy()
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=1e-2, betas=(0.9, 0.99))
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+    losses, accs = [], []
+    model.train()
+    for it in range(30):
+        i = (it * B) % N
+        xb, yb = X[i:i + B], y[i:i + B]
+        opt.zero_grad()
+        o = model(xb)
+        loss = crit(o, yb)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        losses.append(loss.item())
+        accs.append((o.argmax(1) == yb).float().mean().item())
+    out["losses"] = np.array(losses, dtype=np.float64)
+    out["accs"] = np.array(accs, dtype=np.float64)
+    for n, p in model.named_parameters():
+        out["final/" + n] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "trajectory_vit.npz"), **out)
+    print("trajectory_vit: loss %.4f -> %.4f, acc %.2f -> %.2f" % (losses[0], losses[-1], accs[0], accs[-1]))
+
+
+if __name__ == "__main__" and "--trajectory-vit" in sys.argv:
+    torch.set_num_threads(4)
+    trajectory_vit_case()
+    sys.exit(0)
+
 if __name__ == "__main__" and len(sys.argv) > 1:      # python make_golden.py case [case ...]: only those cases
     for name in sys.argv[1:]:
         run_case(name, *CASES[name])
@@ -203,3 +247,4 @@ if __name__ == "__main__":
         preprocessing_case()
         known_answers()
     trajectory_case()
+    trajectory_vit_case()

@@ -210,3 +210,43 @@ def test_thirty_step_trajectory_matches_reference_training_loop():
         err = np.abs(p.detach().cpu().numpy() - ref).max()
         worst = max(worst, err / max(moved, 1e-6))
     assert worst < 5e-2, worst       # 30 Adam steps amplify fp32 rounding; updates themselves are ~30*lr
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_thirty_step_vit_trajectory_matches_reference_training_loop(dtype):
+    """The ViT family of the headline benchmark (patch 16, T = 9): the reference's loop recorded in
+    tests/golden/trajectory_vit.npz vs the fused TrainStep.  fp32: step-for-step; bf16: the losses track the reference
+    within bf16 noise while the trajectories are still close (first 10 steps) and the run converges like it."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "trajectory_vit.npz"))
+    params = {k[len("param/"):]: z[k] for k in z.files if k.startswith("param/")}
+    final = {k[len("final/"):]: z[k] for k in z.files if k.startswith("final/")}
+    model = amc.ViTAMCTransformer(in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=4, d_model=64,
+                                  n_head=8, n_layers=2, ffn_hidden=128, drop_prob=0.0, device=DEV, compute_dtype=dtype)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    ts = TrainStep(model, lr=2e-3, weight_decay=1e-2, betas=(0.9, 0.99), max_norm=1.0, label_smoothing=0.1)
+    X, y = torch.from_numpy(z["X"]).to(DEV), torch.from_numpy(z["y"]).to(DEV)
+    N, B = X.shape[0], 32
+    losses = []
+    for it in range(30):
+        i = (it * B) % N
+        ts.step(X[i:i + B].contiguous(), y[i:i + B].contiguous())
+        loss, acc = ts.read_stats()
+        losses.append(loss)
+        ref = float(z["losses"][it])
+        if dtype == "fp32":
+            assert abs(loss - ref) < 2e-3 * max(1.0, ref), (it, loss, ref)
+            assert abs(acc - float(z["accs"][it])) <= 1.0 / B + 1e-6, (it, acc)
+        elif it < 10:
+            assert abs(loss - ref) < 5e-2 * max(1.0, ref), (it, loss, ref)
+    if dtype == "fp32":
+        worst = 0.0
+        for n, p in model.named_parameters():
+            if n.endswith("w_k.bias"):
+                continue
+            moved = np.abs(final[n] - params[n]).max()
+            worst = max(worst, np.abs(p.detach().cpu().numpy() - final[n]).max() / max(moved, 1e-6))
+        assert worst < 5e-2, worst
+    else:
+        assert abs(np.mean(losses[-5:]) - float(np.mean(z["losses"][-5:]))) < 0.1

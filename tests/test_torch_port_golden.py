@@ -50,3 +50,33 @@ def test_port_dropout_train_mode_runs_and_eval_is_deterministic():
     c = TP.model_forward(src, p, cfg, 0.2, True)
     assert torch.equal(a, b) and not torch.equal(a, c)
     assert TP.predict(src, p, cfg).shape == (4,)
+
+
+@pytest.mark.parametrize("which", ["rawiq", "vit"])
+def test_port_reproduces_the_reference_training_trajectories(which):
+    """30 steps of the reference's own loops (tests/golden/trajectory_*.npz): the port's TrainStep gives the same
+    per-step losses and final weights (multi-step pin: optimizer state, bias correction, clipping)."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, f"trajectory_{which}.npz"))
+    params = {k[len("param/"):]: z[k] for k in z.files if k.startswith("param/")}
+    final = {k[len("final/"):]: z[k] for k in z.files if k.startswith("final/")}
+    if which == "rawiq":
+        cfg = O.Config(kind="rawiq", in_channels=2, seq_length=256, num_classes=4, d_model=32, n_head=4, n_layers=2,
+                       ffn_hidden=64, use_cls_token=True, embedding_type="segment", segment_size=16)
+    else:
+        cfg = O.Config(kind="vit", in_channels=1, img_size_h=32, img_size_w=64, patch_size=16, num_classes=4, d_model=64,
+                       n_head=8, n_layers=2, ffn_hidden=128)
+    p = TP.params_from_numpy(params)
+    ts = TP.TrainStep(p, cfg, drop_prob=0.0, lr=2e-3, weight_decay=1e-2, betas=(0.9, 0.99), max_norm=1.0, label_smoothing=0.1)
+    X, y = torch.from_numpy(z["X"]), torch.from_numpy(z["y"]).long()
+    N, B = X.shape[0], 32
+    for it in range(30):
+        i = (it * B) % N
+        loss, _, _ = ts.step(X[i:i + B], y[i:i + B])
+        assert abs(loss.item() - float(z["losses"][it])) < 1e-4 * max(1.0, float(z["losses"][it])), it
+    for k, ref in final.items():
+        if k.endswith("w_k.bias"):          # dead parameter: its gradient is rounding noise, which Adam turns into lr-size steps
+            continue
+        moved = np.abs(ref - params[k]).max()
+        assert np.abs(p[k].detach().numpy() - ref).max() < 5e-2 * max(moved, 1e-6), k
