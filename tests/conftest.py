@@ -48,6 +48,8 @@ GOLDEN_CASES = {
                                        ffn_hidden=128, use_cls_token=True, embedding_type="segment", segment_size=32)),
     "rawiq_sps2_seg8": ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=32, n_head=2, n_layers=1,
                                       ffn_hidden=64, use_cls_token=True, embedding_type="segment", segment_size=8)),
+    "rawiq_conv1d_1024": ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=32, n_head=2, n_layers=2,
+                                        ffn_hidden=64, use_cls_token=True, embedding_type="conv1d", segment_size=64)),
 }
 GOLDEN_HP = dict(lr=1e-3, weight_decay=1e-2, betas=(0.9, 0.99), clip=1.0, label_smoothing=0.1)
 

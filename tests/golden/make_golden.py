@@ -60,6 +60,10 @@ CASES = {
     "rawiq_sps2_seg8": ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=32, n_head=2, n_layers=1,
                                       ffn_hidden=64, drop_prob=0.0, device="cpu", use_cls_token=True,
                                       embedding_type="segment", segment_size=8), 2),
+    # the long-sequence regime: embedding_type='conv1d' makes every IQ sample a token (T = 1025, K = 2)
+    "rawiq_conv1d_1024": ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=32, n_head=2, n_layers=2,
+                                        ffn_hidden=64, drop_prob=0.0, device="cpu", use_cls_token=True,
+                                        embedding_type="conv1d", segment_size=64), 2),
 }
 
 LR, WD, BETAS, CLIP, LS = 1e-3, 1e-2, (0.9, 0.99), 1.0, 0.1

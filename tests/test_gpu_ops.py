@@ -138,6 +138,51 @@ def test_attention_fwd_bwd(dt, B, T, h, dh, saved):
         assert (dbias.double() - ref_b).abs().max() < (1e-4 if dt == _lib.F32 else 3e-2) * ref_b.abs().max()
 
 
+# T > 288: the flash-style kernels of attn_long.cu (embedding_type='conv1d': T = 1025).  bf16 with head dim 16 / 32 / 64
+# runs the TMA + mma.sync kernels, everything else (fp32, other head dims) the SIMT kernels.  Shapes: the conv1d
+# default (1025 = 8 * 128 + 1: a one-row super-block; 7 chunks of 144 + one of 17 rows), just past the single-CTA
+# limit, whole chunks / super-blocks with no ragged tail (432 = 3 * 144, 384 = 3 * 128), a ragged everything (577).
+@pytest.mark.parametrize("B,T,h,dh", [(2, 1025, 8, 16), (1, 1025, 4, 32), (1, 577, 2, 64), (1, 300, 2, 16),
+                                      (1, 432, 2, 32), (2, 384, 1, 16), (2, 513, 2, 8), (1, 300, 1, 128),
+                                      (1, 1025, 2, 24), (3, 289, 2, 64)])
+@pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
+def test_long_attention_fwd_bwd(dt, B, T, h, dh):
+    d = h * dh
+    g = torch.Generator(device=DEV).manual_seed(T * 31 + dh)
+    qkv = torch.randn(B * T, 3 * d, device=DEV, generator=g).to(tdtype(dt))
+    dout = torch.randn(B * T, d, device=DEV, generator=g).to(tdtype(dt))
+    out = torch.full((B * T, d), float("nan"), device=DEV, dtype=tdtype(dt))
+    dqkv = torch.full((B * T, 3 * d), float("nan"), device=DEV, dtype=tdtype(dt))
+    lse = torch.full((B, h, T), float("nan"), device=DEV)
+    dbias = torch.zeros(3 * d, device=DEV)
+    _lib.check(_lib.lib.amc_attention_fwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), stream()))
+    # inference form (no statistics kept) gives the same output
+    out2 = torch.empty_like(out)
+    _lib.check(_lib.lib.amc_attention_fwd(dt, B, T, h, dh, qkv.data_ptr(), out2.data_ptr(), None, stream()))
+    # the backward of this regime needs the forward's out + lse: asking it to recompute them is an error, not a fallback
+    with pytest.raises(RuntimeError, match="needs the forward"):
+        _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), None, None, dout.data_ptr(),
+                                              dqkv.data_ptr(), None, stream()))
+    _lib.check(_lib.lib.amc_attention_bwd(dt, B, T, h, dh, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                                          dout.data_ptr(), dqkv.data_ptr(), dbias.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = [t.view(B, T, h, dh).transpose(1, 2) for t in x.view(B, T, 3 * d).split(d, dim=-1)]
+    sc = (q @ k.transpose(2, 3)) / math.sqrt(dh)
+    p = torch.softmax(sc, -1)                                            # scale_dot_product_attention.py:26-37
+    ref = (p @ v).transpose(1, 2).reshape(B * T, d)
+    ref.backward(dout.double())
+    tol = 1e-5 if dt == _lib.F32 else 2e-2
+    assert relerr(out.float(), ref.detach()) < tol
+    # log2-domain row statistics: lse2 = log2(sum_j exp(score_ij))
+    ref_lse = torch.logsumexp(sc.detach(), -1) / math.log(2.0)
+    assert (lse.double() - ref_lse).abs().max() < (1e-4 if dt == _lib.F32 else 2e-2)
+    assert relerr(dqkv.float(), x.grad) < tol * (1 if dt == _lib.F32 else 1.5)
+    ref_b = x.grad.sum(0)
+    assert (dbias.double() - ref_b).abs().max() < (1e-4 if dt == _lib.F32 else 3e-2) * ref_b.abs().max()
+
+
 @pytest.mark.parametrize("M,d", [(1000, 128), (77, 256), (513, 512), (64, 16), (33, 96)])
 @pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
 def test_layernorm_fwd_bwd(dt, M, d):

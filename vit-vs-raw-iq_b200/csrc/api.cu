@@ -75,10 +75,12 @@ int validate(const AmcDesc& D, Dims& m) {
     m.has_cls = 1;
   }
   m.T = m.Ttok + m.has_cls;
-  AMC_CHECK_ARG(m.T <= 288, "T=%d tokens per frame exceeds the single-CTA attention limit (288)", m.T);
+  AMC_CHECK_ARG(m.T <= ATTN_LONG_MAX_T, "T=%d tokens per frame unsupported (<= %d)", m.T, ATTN_LONG_MAX_T);
   if (D.dtype == AMC_BF16) {
-    AMC_CHECK_ARG(D.d % 8 == 0 && D.F % 8 == 0 && m.K % 8 == 0,
-                  "bf16 path needs d_model, ffn_hidden and the patch width (%d) to be multiples of 8", m.K);
+    // (a patch width that is not a multiple of 8 -- conv1d embedding, K = 2 -- runs the small-K kernels)
+    AMC_CHECK_ARG(D.d % 8 == 0 && D.F % 8 == 0 && (m.K % 8 == 0 || embed_smallk_supported(m.K)),
+                  "bf16 path needs d_model and ffn_hidden multiples of 8 and a patch width (%d) that is a multiple "
+                  "of 8 or at most 16", m.K);
   }
   if (D.p_drop > 0.f)
     AMC_CHECK_ARG(D.d % 4 == 0 && D.F % 4 == 0, "dropout needs d_model and ffn_hidden multiples of 4");
@@ -343,7 +345,12 @@ struct Model {
     }
     if (!fused) {
       AMC_PROF("patchify", 0.0, (double)m.B * m.Ttok * m.K * (4 + sizeof(E)), patchify<E>(D, m.Ttok, m.K, src, (E*)w.Apatch, st));
-      AMC_TRY(gemm<E>(g, st));
+      if (sizeof(E) == 2 && m.K % 8 != 0) {
+        AMC_PROF("embed_smallk", 2.0 * g.M * g.N * g.K, (double)g.M * (m.K * 2 + m.d * 6),
+                 embed_smallk_fwd(g.M, g.N, g.K, (const bf16*)w.Apatch, (const bf16*)Wemb(), g.epi, st));
+      } else {
+        AMC_TRY(gemm<E>(g, st));
+      }
     }
     if (m.has_cls)
       AMC_PROF("cls_rows", 0.0, 0.0, cls_rows<E>(m.B, m.T, m.d, P(L.cls), pos, (E*)w.x16[0], sizeof(E) == 2 ? w.x32[0] : nullptr, drop, st));
@@ -634,16 +641,22 @@ struct Model {
         if (m.has_cls) AMC_PROF("frontend_bwd_misc", 0.0, 0.0, cls_grad(m.B, m.T, m.d, w.dy32, grads + L.cls, drop, st));
         AMC_PROF("frontend_bwd_misc", 0.0, 0.0, gather_tok_rows<E>(m.B, m.T, m.Ttok, m.d, m.has_cls, w.dy32, (E*)w.demb, drop, st));
         const int Mt = m.B * m.Ttok;
-        if (sizeof(E) != 2) AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
-        GemmArgs g;
-        if (sizeof(E) == 2) g.epi.colsum_out = grads + L.emb_b;
-        g.M = m.d; g.N = m.K; g.K = Mt;
-        g.A = w.demb; g.lda = m.d; g.transA = 1;
-        g.B = w.Apatch; g.ldb = m.K; g.transB = 1;
-        g.split_k = pick_split_k(m.d, m.K, Mt);
-        g.name = "gemm_wgrad";
-        g.epi.D32 = grads + L.emb_w; g.epi.ldd32 = m.K; g.epi.accumulate = 1;
-        AMC_TRY(gemm<E>(g, st));
+        if (sizeof(E) == 2 && m.K % 8 != 0) {
+          AMC_PROF("embed_smallk", 2.0 * Mt * m.d * m.K, (double)Mt * (m.K + m.d) * 2,
+                   embed_smallk_bwd(Mt, m.d, m.K, (const bf16*)w.demb, m.d, (const bf16*)w.Apatch, grads + L.emb_w,
+                                    grads + L.emb_b, st));
+        } else {
+          if (sizeof(E) != 2) AMC_PROF("colsum", 0.0, 0.0, colsum<E>(Mt, m.d, (const E*)w.demb, m.d, grads + L.emb_b, st));
+          GemmArgs g;
+          if (sizeof(E) == 2) g.epi.colsum_out = grads + L.emb_b;
+          g.M = m.d; g.N = m.K; g.K = Mt;
+          g.A = w.demb; g.lda = m.d; g.transA = 1;
+          g.B = w.Apatch; g.ldb = m.K; g.transB = 1;
+          g.split_k = pick_split_k(m.d, m.K, Mt);
+          g.name = "gemm_wgrad";
+          g.epi.D32 = grads + L.emb_w; g.epi.ldd32 = m.K; g.epi.accumulate = 1;
+          AMC_TRY(gemm<E>(g, st));
+        }
       }
     }
     return 0;

@@ -1290,6 +1290,7 @@ inline int pick_warps(int T) { return std::max(1, std::min(8, (T + 7) / 8)); }
 
 template <typename E>
 int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse, cudaStream_t st) {
+  if (T > 32 * MAXJ) return attn_long_fwd<E>(B, T, h, dh, qkv, out, lse, st);   // outside the single-CTA regime
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;
@@ -1383,6 +1384,7 @@ template <typename E>
 int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* out, const float* lse, const E* dout, E* dqkv,
                        float* dbias, bool* fused, cudaStream_t st) {
   *fused = false;
+  if (T > 32 * MAXJ) return attn_long_bwd<E>(B, T, h, dh, qkv, out, lse, dout, dqkv, st);
   AMC_CHECK_ARG(T >= 1 && T <= 32 * MAXJ, "attention_bwd: T=%d unsupported (1..%d tokens per frame)", T, 32 * MAXJ);
   AMC_CHECK_ARG(dh >= 1 && dh <= 128, "attention_bwd: head dim %d unsupported (1..128)", dh);
   if (B == 0) return 0;

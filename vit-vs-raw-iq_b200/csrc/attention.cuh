@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -19,6 +20,15 @@ bool attn_tiles_supported(int T, int h, int dh);
 int attn_tiles_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float* lse, bool* handled, cudaStream_t st);
 int attn_tiles_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out, const float* lse, const bf16* dout,
                    bf16* dqkv, float* dbias, bool* handled, cudaStream_t st);
+
+// attn_long.cu: T > 288 (embedding_type='conv1d': one token per IQ sample) -- flash-style tiled kernels; the
+// backward needs the forward's `out` and `lse`
+constexpr int ATTN_LONG_MAX_T = 16384;
+template <typename E>
+int attn_long_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse, cudaStream_t st);
+template <typename E>
+int attn_long_bwd(int B, int T, int h, int dh, const E* qkv, const E* out, const float* lse, const E* dout, E* dqkv,
+                  cudaStream_t st);
 
 // attn_cls.cu: attention restricted to query row 0 (the CLS token) for the top layer of a CLS-pooled model (bf16)
 bool attn_cls_supported(int T, int h, int dh);

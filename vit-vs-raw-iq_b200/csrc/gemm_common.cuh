@@ -139,6 +139,11 @@ struct GemmArgs {
 int gemm_f32(const GemmArgs& g, cudaStream_t st);   // gemm_simt.cu
 int gemm_bf16(const GemmArgs& g, cudaStream_t st);  // gemm_tc.cu (tcgen05)
 
+// embed_smallk.cu: bf16 embedding whose patch width K is not a multiple of 8 (conv1d embedding: K = 2)
+bool embed_smallk_supported(int K);
+int embed_smallk_fwd(int M, int N, int K, const bf16* A, const bf16* W, const Epi& epi, cudaStream_t st);
+int embed_smallk_bwd(int M, int N, int K, const bf16* dY, int ldy, const bf16* A, float* dW, float* db, cudaStream_t st);
+
 // frontend_tc.cu: fused normalise + frame + patchify + embedding GEMM (+bias, +PE, dropout) for the bf16 path.
 // *handled = false when the geometry is outside what the fused kernel covers (caller: patchify + gemm);
 // probe_only = true answers that question without launching.
