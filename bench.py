@@ -61,6 +61,12 @@ WORKLOADS = {
                                  kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=512, n_head=8,
                                          n_layers=12, ffn_hidden=2048, drop_prob=0.2, use_cls_token=True,
                                          embedding_type="segment", segment_size=16)),
+    # the reference constructor's default embedding (R/models/transformer_rawIQ.py:25): Conv1d(2, d, 1), one token per
+    # IQ sample -> T = 1025, long-sequence attention (attn_long.cu) + small-K embedding; train.py's other defaults
+    "rawiq_conv1d_d128_L6": dict(kind="rawiq", batch=128, lr=1e-4, wd=1e-4,
+                                 kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8,
+                                         n_layers=6, ffn_hidden=1024, drop_prob=0.2, use_cls_token=True,
+                                         embedding_type="conv1d", segment_size=64)),
 }
 DEFAULT_WORKLOAD = "vit_p16_d256_L6"
 
@@ -72,8 +78,9 @@ def geometry(w):
         kemb = kw["in_channels"] * kw["patch_size"] ** 2
         T = ttok + 1
     else:
-        ttok = kw["seq_length"] // kw["segment_size"]
-        kemb = kw["in_channels"] * kw["segment_size"]
+        seg = 1 if kw.get("embedding_type", "segment") == "conv1d" else kw["segment_size"]
+        ttok = kw["seq_length"] // seg
+        kemb = kw["in_channels"] * seg
         T = ttok + (1 if kw.get("use_cls_token", True) else 0)
     return T, ttok, kemb
 

@@ -33,6 +33,7 @@ CLASS_OF = [
     (r"ln_bwd_vec_kernel", "ln_bwd"),
     (r"attn_(frames|mma|tile|tc)_bwd_kernel", "attn_bwd"),
     (r"attn_(frames|mma|tile|tc)_fwd_kernel", "attn_fwd"),
+    (r"attn_long(_mma)?_fwd_kernel", "attn_fwd"),
     (r"patchify", "patchify"),
     (r"adamw_kernel", "adamw_clip"),
 ]
