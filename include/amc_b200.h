@@ -182,6 +182,15 @@ int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, v
 int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* out, const float* lse,
                       const void* dout, void* dqkv, float* dbias, amc_stream_t stream);
 
+/* The same attention restricted to query row 0 of every frame, bf16, head dim 16 / 32 / 64: what the TOP encoder layer
+ * of a CLS-pooled model needs, since only `x[:, 0]` feeds the classifier head (R/models/transformer_rawIQ.py:88-90,
+ * V/models/amc_transformer.py:29).  fwd writes row 0 of every frame of `out` ([B*T, d], other rows untouched);
+ * bwd reads row 0 of every frame of `dout` and writes all of dqkv (dq of the other rows is exactly zero);
+ * dbias (nullable, fp32 [3d]) += q | k | v bias gradients (the k part is exactly zero). */
+int amc_attention_cls_fwd(int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream);
+int amc_attention_cls_bwd(int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv, float* dbias,
+                          amc_stream_t stream);
+
 /* y = gamma * (u - mean) / sqrt(var_biased + eps) + beta over the last dim (layers_norm.py:11-19).
  *   u fp32 [M,d]; y16 (dtype) / y32 (fp32) / xhat (dtype) / rstd (fp32 [M]) may each be NULL. */
 int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamma, const float* beta, float eps,

@@ -183,6 +183,39 @@ def test_long_attention_fwd_bwd(dt, B, T, h, dh):
     assert (dbias.double() - ref_b).abs().max() < (1e-4 if dt == _lib.F32 else 3e-2) * ref_b.abs().max()
 
 
+# Query row 0 only (the top layer of a CLS-pooled model): register-resident kernels for T <= 288, the streaming
+# warp-per-(frame, head) kernels above that (conv1d: T = 1025).
+@pytest.mark.parametrize("B,T,h,dh", [(3, 9, 8, 32), (2, 65, 8, 16), (5, 129, 4, 64), (2, 257, 8, 32), (1, 288, 2, 16),
+                                      (4, 1025, 8, 16), (2, 1025, 4, 32), (3, 577, 2, 64), (2, 289, 2, 16),
+                                      (40, 300, 3, 16)])
+def test_cls_row_attention_fwd_bwd(B, T, h, dh):
+    d = h * dh
+    g = torch.Generator(device=DEV).manual_seed(T * 17 + dh)
+    qkv = torch.randn(B * T, 3 * d, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B * T, d, device=DEV, generator=g).bfloat16()       # only row 0 of every frame is read
+    out = torch.full((B * T, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dqkv = torch.full((B * T, 3 * d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dbias = torch.zeros(3 * d, device=DEV)
+    _lib.check(_lib.lib.amc_attention_cls_fwd(B, T, h, dh, qkv.data_ptr(), out.data_ptr(), stream()))
+    _lib.check(_lib.lib.amc_attention_cls_bwd(B, T, h, dh, qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                                              dbias.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = [t.view(B, T, h, dh).transpose(1, 2) for t in x.view(B, T, 3 * d).split(d, dim=-1)]
+    p = torch.softmax((q[:, :, :1] @ k.transpose(2, 3)) / math.sqrt(dh), -1)     # [B, h, 1, T]
+    ref = (p @ v).transpose(1, 2).reshape(B, d)
+    go = dout.view(B, T, d)[:, 0].double()
+    ref.backward(go)
+    got = out.view(B, T, d)[:, 0].float()
+    assert relerr(got, ref.detach()) < 2e-2
+    assert torch.isnan(out.view(B, T, d)[:, 1:].float()).all()                    # other rows are not touched
+    assert not torch.isnan(dqkv.float()).any()                                    # dqkv is written completely
+    assert relerr(dqkv.float(), x.grad) < 3e-2
+    assert (dqkv.view(B, T, 3 * d)[:, 1:, :d] == 0).all()                         # dead queries
+    ref_b = x.grad.sum(0)
+    assert (dbias.double() - ref_b).abs().max() < 3e-2 * ref_b.abs().max()
+
+
 @pytest.mark.parametrize("M,d", [(1000, 128), (77, 256), (513, 512), (64, 16), (33, 96)])
 @pytest.mark.parametrize("dt", [_lib.F32, _lib.BF16])
 def test_layernorm_fwd_bwd(dt, M, d):

@@ -67,6 +67,8 @@ def _load():
         "amc_gemm_relu_mask": [i32, i32, i32, vp, i32, vp, i32, vp, f32, vp, vp],
         "amc_attention_fwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp],
         "amc_attention_bwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+        "amc_attention_cls_fwd": [i32, i32, i32, i32, vp, vp, vp],
+        "amc_attention_cls_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "amc_layernorm_fwd": [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp],
         "amc_layernorm_bwd": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "amc_frontend_fwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp],

@@ -789,6 +789,20 @@ int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, v
     return attention_fwd<bf16>(B, T, h, dh, (const bf16*)qkv, (bf16*)out, lse, (cudaStream_t)stream);
   return attention_fwd<float>(B, T, h, dh, (const float*)qkv, (float*)out, lse, (cudaStream_t)stream);
 }
+int amc_attention_cls_fwd(int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream) {
+  AMC_CHECK_ARG(qkv && out, "NULL argument");
+  AMC_CHECK_ARG((h * dh) % 8 == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "attention_cls: rows must be 16-byte aligned");
+  return attn_cls_fwd(B, T, h, dh, (const bf16*)qkv, (bf16*)out, (cudaStream_t)stream);
+}
+int amc_attention_cls_bwd(int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv, float* dbias,
+                          amc_stream_t stream) {
+  AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
+  AMC_CHECK_ARG((h * dh) % 8 == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) |
+                                       reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
+                "attention_cls: rows must be 16-byte aligned");
+  return attn_cls_bwd(B, T, h, dh, (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, dbias, (cudaStream_t)stream);
+}
 int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* out, const float* lse,
                       const void* dout, void* dqkv, float* dbias, amc_stream_t stream) {
   AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
