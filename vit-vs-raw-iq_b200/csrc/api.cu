@@ -11,7 +11,7 @@
 
 namespace amc {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -671,7 +671,7 @@ using namespace amc;
 extern "C" {
 
 int amc_abi_version(void) { return AMC_ABI_VERSION; }
-long long amc_launch_count(void) { return g_launch_count; }
+long long amc_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 const char* amc_last_error(void) { return g_err; }
 
 int amc_param_layout(const AmcDesc* desc, AmcParamLayout* out) {

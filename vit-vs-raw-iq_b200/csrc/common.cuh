@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/amc_b200.h"
@@ -31,10 +32,11 @@ void set_error(const char* fmt, ...);
       return (int)e__;                                                                    \
     }                                                                                     \
   } while (0)
-extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<long long> g_launch_count;   // kernels launched by this library (bench.py's gpu_launches); autograd
+                                                 // calls backward from its own thread, hence atomic
 #define AMC_LAUNCH_CHECK()          \
   do {                              \
-    ++::amc::g_launch_count;        \
+    ::amc::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
     AMC_CUDA(cudaGetLastError());   \
   } while (0)
 #define AMC_TRY(expr)          \
