@@ -1,0 +1,52 @@
+#!/usr/bin/env bash
+# One gpurun call = one round's GPU evidence (a call costs ~30 s of box time before the command starts, so batch):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh collect r2'     # on the B200 box
+#   bash tools/gpu_round.sh summarise r2                                                   # back here: -> profiles/
+# collect: GPU tests, smoke, the default bench line (+ reference arm), one bench line per other workload, the ncu launch
+# list of one training step and one `ncu --set full` capture of that step (each ncu pass only after the same command
+# has exited 0 without ncu; nothing printed under ncu is a benchmark number).  Every step has its own timeout so a hang
+# cannot eat the box.  Outputs: gpurun_out/<tag>_*.
+set -u
+MODE=${1:-collect}
+TAG=${2:-rX}
+OUT=gpurun_out
+mkdir -p "$OUT"
+WORKLOADS="rawiq_seg16_d128_L6 vit_p4_d128_L6 rawiq_sps1_seg8_d256_L6 rawiq_sps2_seg8_d256_L6 rawiq_seg16_d512_L12 rawiq_conv1d_d128_L6"
+
+if [ "$MODE" = collect ]; then
+  timeout 400 python -m pytest tests -m gpu -q -x > "$OUT/${TAG}_pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 120 python __graft_entry__.py smoke > "$OUT/${TAG}_smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 300 python bench.py > "$OUT/${TAG}_bench_1gpu.json" 2> "$OUT/${TAG}_bench_1gpu.err"; echo "bench rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_reference_arm.json" 2>> "$OUT/${TAG}_bench_1gpu.err"
+  echo "reference arm rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  for W in $WORKLOADS; do
+    timeout 120 python bench.py --workload "$W" --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_wl_${W}.json" 2>> "$OUT/${TAG}_wl.err"
+    echo "workload $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  done
+  if timeout 120 python tools/one_step.py > "$OUT/${TAG}_one_step_plain.log" 2>&1; then
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file "$OUT/${TAG}_launches_train.csv" python tools/one_step.py > "$OUT/${TAG}_ncu_launch.log" 2>&1
+    echo "ncu launch list rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+    timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
+      -o "$OUT/${TAG}_full_step" python tools/one_step.py --batch 8192 > "$OUT/${TAG}_ncu_full.log" 2>&1
+    echo "ncu full rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  else
+    echo "one_step.py failed without ncu: no ncu passes" | tee -a "$OUT/${TAG}_status.txt"
+  fi
+  nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/${TAG}_nvidia_smi.csv" 2>&1
+  cat "$OUT/${TAG}_status.txt"
+elif [ "$MODE" = summarise ]; then
+  cp "$OUT/${TAG}_bench_1gpu.json" "profiles/${TAG}_bench_1gpu.json"
+  cp "$OUT/${TAG}_bench_reference_arm.json" "profiles/${TAG}_bench_reference_arm.json"
+  for W in $WORKLOADS; do
+    [ -s "$OUT/${TAG}_wl_${W}.json" ] && cp "$OUT/${TAG}_wl_${W}.json" "profiles/workloads/${TAG}_wl_${W}.json"
+  done
+  [ -s "$OUT/${TAG}_launches_train.csv" ] && cp "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.csv" && \
+    python tools/ncu_summary.py launches "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.md" \
+      --title "${TAG}: ncu launch list of one training step (tools/one_step.py, default workload)"
+  [ -s "$OUT/${TAG}_full_step.ncu-rep" ] && \
+    python tools/ncu_summary.py full "$OUT/${TAG}_full_step.ncu-rep" "profiles/${TAG}_ncu_full_step.json"
+  tail -3 "$OUT/${TAG}_pytest_gpu.log"
+else
+  echo "usage: $0 collect|summarise <tag>"; exit 2
+fi
