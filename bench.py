@@ -61,7 +61,7 @@ WORKLOADS = {
                                  kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=512, n_head=8,
                                          n_layers=12, ffn_hidden=2048, drop_prob=0.2, use_cls_token=True,
                                          embedding_type="segment", segment_size=16)),
-    # the reference constructor's default embedding (R/models/transformer_rawIQ.py:25): Conv1d(2, d, 1), one token per
+    # the reference Encoder's default embedding (R/models/encoder.py:26,34-41): Conv1d(2, d, 1), one token per
     # IQ sample -> T = 1025, long-sequence attention (attn_long.cu) + small-K embedding; train.py's other defaults
     "rawiq_conv1d_d128_L6": dict(kind="rawiq", batch=128, lr=1e-4, wd=1e-4,
                                  kw=dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8,

@@ -111,7 +111,7 @@ def test_golden_logits_grads_and_train_step(name, dtype):
                  n_layers=2, ffn_hidden=512), 7),
     ("rawiq", dict(in_channels=2, seq_length=2048, num_classes=11, d_model=256, n_head=8, n_layers=1,
                    ffn_hidden=1024, use_cls_token=True, embedding_type="segment", segment_size=8), 3),
-    # the reference constructor's default embedding: one token per IQ sample (T = 1025, K = 2), long-sequence attention
+    # the reference Encoder's default embedding (R/models/encoder.py:26): one token per IQ sample (T = 1025, K = 2), long-sequence attention
     ("rawiq", dict(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8, n_layers=2,
                    ffn_hidden=256, use_cls_token=True, embedding_type="conv1d", segment_size=64), 2),
     ("rawiq", dict(in_channels=2, seq_length=512, num_classes=11, d_model=64, n_head=2, n_layers=1,

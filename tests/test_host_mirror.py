@@ -141,3 +141,27 @@ def test_layout_and_workspace_host_calls():
     bad.h = 7
     with pytest.raises(ValueError, match="divisible"):
         _lib.param_layout(bad)
+
+
+def test_conv1d_embedding_envelope_host_calls():
+    """embedding_type='conv1d' (the reference Encoder's default, R/models/encoder.py:26): one token per IQ sample -> T = seq_length + 1, K = 2.  Both
+    arithmetic modes accept it (long-sequence attention + small-K embedding); past 16384 tokens the layout call refuses."""
+    m = amc.RawIQAMCTransformer(in_channels=2, seq_length=1024, num_classes=11, d_model=128, n_head=8, n_layers=2,
+                                ffn_hidden=256, drop_prob=0.1, device="cpu", embedding_type="conv1d")
+    core = m._core
+    L = core.layout
+    assert (L.T, L.Ttok, L.K_embed) == (1025, 1024, 2)
+    assert m.encoder.sequence_embedding.projection.weight.shape == (128, 2, 1)          # Conv1d(2, d, kernel_size=1)
+    assert m.encoder.positional_encoding.encoding.shape == (1025, 128)
+    for dt in (_lib.F32, _lib.BF16):
+        assert _lib.workspace_bytes(core._desc(B=4, dtype=dt, training=True)) > _lib.workspace_bytes(
+            core._desc(B=4, dtype=dt, training=False)) > 0
+    too_long = core._desc(B=1, dtype=_lib.BF16)
+    too_long.seq_len = 20000
+    with pytest.raises(ValueError, match="tokens per frame unsupported"):
+        _lib.param_layout(too_long)
+    odd = core._desc(B=1, dtype=_lib.BF16)
+    odd.in_ch, odd.seg = 3, 7                                                            # K = 21: neither % 8 nor <= 16
+    odd.seq_len = 1022
+    with pytest.raises(ValueError, match="patch width"):
+        _lib.param_layout(odd)
