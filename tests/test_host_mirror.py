@@ -165,3 +165,31 @@ def test_conv1d_embedding_envelope_host_calls():
     odd.seq_len = 1022
     with pytest.raises(ValueError, match="patch width"):
         _lib.param_layout(odd)
+
+
+def test_error_text_is_thread_local():
+    """autograd calls backward from its own thread, so the error text behind a non-zero return must belong
+    to the calling thread (`amc_last_error` is thread-local)."""
+    import threading
+    core = build_ours("vit_p16")._core
+    seen = {}
+    barrier = threading.Barrier(2)
+
+    def worker(tag, mutate, expect):
+        d = core._desc(B=2, dtype=_lib.F32)
+        mutate(d)
+        out = _lib.AmcParamLayout()
+        for _ in range(200):
+            rc = _lib.lib.amc_param_layout(ctypes.byref(d), ctypes.byref(out))
+            barrier.wait()
+            msg = _lib.lib.amc_last_error().decode()
+            if rc == 0 or expect not in msg:
+                seen[tag] = msg
+                barrier.abort()
+                return
+        seen[tag] = "ok"
+
+    a = threading.Thread(target=worker, args=("a", lambda d: setattr(d, "h", 7), "divisible by n_head"))
+    b = threading.Thread(target=worker, args=("b", lambda d: setattr(d, "kind", 99), "unknown model kind"))
+    a.start(); b.start(); a.join(); b.join()
+    assert seen == {"a": "ok", "b": "ok"}, seen
