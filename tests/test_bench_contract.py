@@ -37,6 +37,11 @@ def test_algorithmic_flops_match_the_survey_table():
     for name, gf in expect.items():
         got = bench.flops_per_frame(bench.WORKLOADS[name]) / 1e9
         assert abs(got - gf) / gf < 5e-3, (name, got, gf)
+    # conv1d embedding: one token per IQ sample (T = 1025, K = 2); the §8(d) formula L*T*(8d^2 + 4dF + 4Td) + 2*Ttok*K*d + 2dC
+    w = bench.WORKLOADS["rawiq_conv1d_d128_L6"]
+    assert bench.geometry(w) == (1025, 1024, 2)
+    d, F, T = 128, 1024, 1025
+    assert bench.flops_per_frame(w) == 6 * T * (8 * d * d + 4 * d * F + 4 * T * d) + 2 * 1024 * 2 * d + 2 * d * 11
 
 
 def test_ncu_launch_list_summary_parses_the_committed_capture(tmp_path):
