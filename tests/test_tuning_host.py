@@ -1,6 +1,6 @@
 """Host logic of the repaired hyper-parameter search (vit-vs-raw-iq_b200/tuning.py; TT/hyperparameter_tuning.py is
 its contract): bounds, position repair, the two constructor contracts, the swarm optimiser and the
-rank-sharded fitness evaluation (gloo, world_size 2).  The training half (`fast_train`) needs a GPU: test_gpu_tuning.py."""
+rank-sharded fitness evaluation (gloo, world_size 2).  The training half (`fast_train`) needs a GPU: test_tuning_gpu.py."""
 import os
 import socket
 
