@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # One gpurun call = one round's GPU evidence (a call costs ~30 s of box time before the command starts, so batch):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh collect r2'     # on the B200 box
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh sanitize r2'    # compute-sanitizer subset
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh sanitize r2 memcheck'   # compute-sanitizer subset (one tool per call: memcheck | racecheck)
 #   bash tools/gpu_round.sh summarise r2                                                   # back here: -> profiles/
 # collect: GPU tests, smoke, the default bench line (+ reference arm), one bench line per other workload, the ncu launch
 # list of one training step and one `ncu --set full` capture of that step (each ncu pass only after the same command
@@ -40,7 +40,8 @@ elif [ "$MODE" = sanitize ]; then
   # memcheck + racecheck over the op-level tests at their smallest shapes (the sanitizer slows kernels
   # 10-100x: a bounded subset, each tool under its own timeout).  gpurun --timeout 900 -- 'bash tools/gpu_round.sh sanitize r2'
   SEL="test_attention_fwd_bwd and (3-9-8-32 or 2-65-8-16 or 1-257-8-32) or test_long_attention_fwd_bwd and 1-300-2-16 or test_cls_row and (3-9-8-32 or 2-289-2-16) or test_layernorm_fwd_bwd and 64-16 or test_gemm_epilogues"
-  for TOOL in memcheck racecheck; do
+  # one tool per gpurun call (B200_PROFILING.md: several sanitizer tools in one call have left the GPU unusable)
+  for TOOL in ${3:-memcheck}; do
     timeout 400 compute-sanitizer --tool $TOOL --error-exitcode 9 --log-file "$OUT/${TAG}_sanitizer_${TOOL}.log" \
       python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "$SEL" > "$OUT/${TAG}_sanitizer_${TOOL}_pytest.log" 2>&1
     echo "compute-sanitizer $TOOL rc=$?" | tee -a "$OUT/${TAG}_status.txt"

@@ -1245,6 +1245,12 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(TcGeom gm, const bf16*
   if (tid == 0) bulk_wait_all0();
 }
 
+// A/B switch for kernel studies (tools/probes/attn_tc5_check.py): AMC_ATTN_LEGACY=1 skips the tcgen05 kernels
+inline bool attn_legacy_only() {
+  static const bool v = [] { const char* e = getenv("AMC_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  return v;
+}
+
 inline bool use_tc(int T, int h, int dh) {
   return T > 16 && T <= 288 && (dh == 16 || dh == 32 || dh == 64) && (h * dh) % 8 == 0;
 }
@@ -1315,6 +1321,8 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse,
   }
   if constexpr (std::is_same<E, bf16>::value) {
     bool handled = false;
+    if (!attn_legacy_only()) AMC_TRY(attn_tc5_fwd(B, T, h, dh, qkv, out, lse, &handled, st));
+    if (handled) return 0;
     AMC_TRY(attn_tiles_fwd(B, T, h, dh, qkv, out, lse, &handled, st));
     if (handled) return 0;
   }
