@@ -133,6 +133,8 @@ SHAPES = [(2, 65, 8, 16), (3, 65, 8, 16), (2, 129, 8, 16), (2, 129, 8, 32), (2, 
           (700, 65, 8, 16)]
 TIMED = [(1024, 129, 8, 32), (2048, 65, 8, 16), (512, 257, 8, 32), (1024, 129, 8, 16), (2048, 65, 8, 64)]
 
+os.environ.setdefault("AMC_ATTN_TC5", "all")      # study the tcgen05 kernels on every shape they support
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--bwd", action="store_true")

@@ -1418,8 +1418,11 @@ int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* out, 
   }
   if constexpr (std::is_same<E, bf16>::value) {
     bool handled = false;
-    if (!attn_legacy_only()) AMC_TRY(attn_tc5_bwd(B, T, h, dh, qkv, out, lse, dout, dqkv, &handled, st));
-    if (handled) return 0;      // (*fused stays false: the bias gradients come from the column-sum pass)
+    if (!attn_legacy_only()) AMC_TRY(attn_tc5_bwd(B, T, h, dh, qkv, out, lse, dout, dqkv, dbias, &handled, st));
+    if (handled) {
+      *fused = true;
+      return 0;
+    }
     AMC_TRY(attn_tiles_bwd(B, T, h, dh, qkv, out, lse, dout, dqkv, dbias, &handled, st));
     if (handled) {
       *fused = true;

@@ -24,9 +24,9 @@ int attn_tiles_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out
 // attn_tc5.cu: tcgen05 / TMEM kernels for 49 <= T <= 272 (bf16, head dim 16 / 32 / 64); *handled = false -> next kernel
 bool attn_tc5_supported(int T, int h, int dh);
 int attn_tc5_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float* lse, bool* handled, cudaStream_t st);
-// (needs the forward's out + lse; the q | k | v bias gradients are left to the caller's column-sum pass)
+// (needs the forward's out + lse; dbias (nullable, fp32 [3d]) += q | k | v bias gradients)
 int attn_tc5_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out, const float* lse, const bf16* dout,
-                 bf16* dqkv, bool* handled, cudaStream_t st);
+                 bf16* dqkv, float* dbias, bool* handled, cudaStream_t st);
 
 // attn_long.cu: T > 288 (embedding_type='conv1d': one token per IQ sample) -- flash-style tiled kernels; the
 // backward needs the forward's `out` and `lse`

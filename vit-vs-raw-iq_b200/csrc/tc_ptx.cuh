@@ -35,7 +35,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+#ifdef AMC_MBAR_BACKOFF_NS
+    __nanosleep(AMC_MBAR_BACKOFF_NS);
+#endif
+    if (++spins > (1u << 24)) {
+#ifdef AMC_MBAR_DEBUG
+      printf("mbar timeout: block %d thread %d barrier smem offset %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar) & 0x3ffu, parity);
+#endif
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
