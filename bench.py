@@ -2,7 +2,7 @@
 """bench.py -- IQ frames/s of the encoder hot path (BASELINE.json metric) on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
-    python bench.py --impl reference --steps K --warmup W     # reference arm: CPU port of the reference path
+    python bench.py --impl reference --steps K --warmup W     # reference arm: the unmodified reference (oracle/_ref) on the host cores
 
 A "step" is one training step (zero_grad -> forward -> CE(label_smoothing) -> backward -> clip -> AdamW,
 R/training/train.py:258-271) over one batch of synthetic RadioML-shaped frames (random-init weights).
@@ -147,8 +147,9 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# Reference arm / CPU baseline: the PyTorch-eager port of the reference path (oracle/amc_torch_port.py:
-# the same ATen operators the reference's modules issue, dropout included) on the host cores
+# Reference arm / CPU baseline: the unmodified reference modules (oracle/_ref, vendored by oracle/make_ref.py) on the host
+# cores; when they did not travel, the PyTorch-eager port of the reference path (oracle/amc_torch_port.py: the same ATen
+# operators the reference's modules issue, dropout included)
 # ------------------------------------------------------------------------------------------------
 def port_setup(w, sample_frames, device="cpu", seed=0):
     import torch
@@ -166,20 +167,72 @@ def port_setup(w, sample_frames, device="cpu", seed=0):
     return ts, src, labels
 
 
-def cpu_port_train_frames_per_s(w, sample_frames, steps, warmup):
-    """Train steps of the torch port on all host threads -> (frames/s, s/step, threads)."""
+class ReferenceStep:
+    """The reference's own training step on its own, unmodified modules (vendored into oracle/_ref by oracle/make_ref.py):
+    R/training/train.py:258-271 verbatim -- zero_grad, model(x), CrossEntropyLoss(label_smoothing=0.1), backward,
+    clip_grad_norm_(1.0), AdamW(betas (0.9, 0.99)).step() -- model.train(), dropout as configured."""
+
+    def __init__(self, w, device="cpu", seed=0):
+        import torch
+        from oracle.make_ref import load_reference
+        classes = load_reference()
+        if classes is None:
+            raise FileNotFoundError("oracle/_ref is absent (python oracle/make_ref.py in the build container)")
+        RawIQ, ViT = classes
+        torch.manual_seed(seed)
+        self.model = (ViT if w["kind"] == "vit" else RawIQ)(**w["kw"], device=device).to(device)
+        self.model.train()
+        self.criterion = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=w["lr"], weight_decay=w["wd"], betas=(0.9, 0.99))
+        self.torch = torch
+
+    def step(self, images, labels):
+        self.opt.zero_grad()
+        outputs = self.model(images)
+        loss = self.criterion(outputs, labels)
+        loss.backward()
+        self.torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=1.0)
+        self.opt.step()
+        return loss
+
+
+def reference_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json"))
+
+
+def cpu_train_frames_per_s(w, sample_frames, steps, warmup):
+    """Train steps on all host threads -> (frames/s, s/step, threads, kind): the unmodified reference when oracle/_ref
+    travelled with the snapshot ("reference"), else the torch port of its operator sequence ("port")."""
     import torch
     n = os.cpu_count() or 1
     torch.set_num_threads(n)
-    ts, src, labels = port_setup(w, sample_frames)
+    if reference_available():
+        kind = "reference"
+        kw = w["kw"]
+        g = torch.Generator().manual_seed(0)
+        shape = (sample_frames, 1, 32, 64) if w["kind"] == "vit" else (sample_frames, 2, kw["seq_length"])
+        src = torch.randn(shape, generator=g)
+        labels = torch.randint(0, kw["num_classes"], (sample_frames,), generator=g)
+        ref = ReferenceStep(w)
+        step = lambda: ref.step(src, labels)
+    else:
+        kind = "port"
+        ts, src, labels = port_setup(w, sample_frames)
+        step = lambda: ts.step(src, labels)[0]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        loss, _, _ = ts.step(src, labels)
+        loss = step()
         loss.item()                                   # the reference reads loss.item() every step
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return sample_frames * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
+    return sample_frames * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads(), kind
+
+
+KIND_NOTE = {"reference": "the unmodified reference modules (oracle/_ref) and its train step (R/training/train.py:258-271): "
+                          "fp32, dropout on, torch CPU eager, all host threads",
+             "port": "PyTorch-eager CPU port (oracle/amc_torch_port.py) of the reference train step: same ATen operators, "
+                     "dropout on, fp32, all host threads (oracle/_ref was not vendored)"}
 
 
 def gpu_eager_port_frames_per_s(w, frames, dev, steps=5, warmup=2):
@@ -211,16 +264,14 @@ def run_reference_arm(args, w, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.cpu_sample
-    fps, sec, cores = cpu_port_train_frames_per_s(w, sample, args.steps, max(args.warmup, 1))
+    sample = args.batch or args.cpu_sample       # --batch runs the reference arm at a stated per-step batch
+    fps, sec, cores, kind = cpu_train_frames_per_s(w, sample, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, "frames_per_step": sample, "note":
-                   "PyTorch-eager CPU port (oracle/amc_torch_port.py) of the reference train step: same ATen operators, "
-                   "dropout on, fp32, all host threads"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+        "config": {"workload": wname, "frames_per_step": sample, "note": KIND_NOTE[kind]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} train steps of {sample} frames, torch CPU eager on {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -453,12 +504,12 @@ def main():
                                   "reference sets it, fp32 weights, dropout on); reported beside, not the target"}
     if not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        fps, sec, cores = cpu_port_train_frames_per_s(w, args.cpu_sample, 2, 1)
+        fps, sec, cores, kind = cpu_train_frames_per_s(w, args.cpu_sample, 2, 1)
         n_steps = max(2, min(40, int(12.0 / max(sec, 1e-3))))
-        fps, sec, cores = cpu_port_train_frames_per_s(w, args.cpu_sample, n_steps, 1)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_steps} train steps of {args.cpu_sample} frames (torch CPU eager port of "
-                                          f"the reference ops, dropout on, fp32), {time.perf_counter() - t0:.0f} s total"}
+        fps, sec, cores, kind = cpu_train_frames_per_s(w, args.cpu_sample, n_steps, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                                "sample": f"{n_steps} train steps of {args.cpu_sample} frames ({KIND_NOTE[kind]}), "
+                                          f"{time.perf_counter() - t0:.0f} s total"}
     print(json.dumps(line), flush=True)
     if args.profile_out:
         with open(args.profile_out, "w") as f:

@@ -128,7 +128,9 @@ int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, vo
 
 /* nn.CrossEntropyLoss(label_smoothing) + argmax statistics (R/training/train.py:260,274-277,504).
  *   stats[0] += sum of per-frame losses * loss_scale, stats[1] += #correct (fp32 accumulators)
- *   dlogits = (softmax - smoothed one-hot) * grad_scale   (grad_scale = 1/global_batch) */
+ *   dlogits = (softmax - smoothed one-hot) * grad_scale   (grad_scale = 1/global_batch)
+ *   labels: device int64 [B].  A label outside [0, C) -- where the reference raises -- makes that frame's loss NaN, so
+ *   stats[0] is NaN from then on and the host mirror raises when it reads the statistics. */
 int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float label_smoothing,
                 float grad_scale, float loss_scale, float* dlogits, float* stats, amc_stream_t stream);
 

@@ -49,11 +49,11 @@ def check_grads(model, ref_grads, dtype):
             continue
         e = l2_rel(g, r)
         tol = GRAD_TOL[dtype]
-        if dtype == "bf16" and ".ffn.linear1." in n:
+        if dtype == "bf16" and ".ffn.linear1." in n and model._core.d <= 64:
             # d(linear1) = (dH * ReLU mask)^T x1: hidden pre-activations within bf16 rounding of zero flip their mask
-            # bit, and the L2 error goes like sqrt(flipped fraction).  On these d <= 64 fixtures torch's own bf16
-            # autocast shows 5-6 % on exactly these tensors (2.8-3.6 % at the reference's sizes);
-            # every other tensor, including the ones fed through this mask, stays inside 6e-2.
+            # bit, and the L2 error goes like sqrt(flipped fraction).  On the d <= 64 fixtures torch's own bf16
+            # autocast shows 5-6 % on exactly these tensors; at the reference's sizes (d >= 128) it is 2.8-3.6 %
+            #  and the stated 6e-2 applies there, as to every other tensor.
             tol = 0.12
         assert e < tol, (n, e)
         num += float(((g.astype(np.float64) - r) ** 2).sum())

@@ -250,3 +250,51 @@ def test_thirty_step_vit_trajectory_matches_reference_training_loop(dtype):
         assert worst < 5e-2, worst
     else:
         assert abs(np.mean(losses[-5:]) - float(np.mean(z["losses"][-5:]))) < 0.1
+
+
+def test_labels_are_validated_like_cross_entropy_loss():
+    """nn.CrossEntropyLoss (R/training/train.py:260) raises on a wrong label dtype / length / device and on a target
+    outside [0, C); TrainStep rejects the former up front and the kernel turns the latter into a NaN loss that the host
+    raises on when it reads the statistics."""
+    z, params, _, _ = load_golden("vit_p16")
+    model = build("vit_p16", "fp32")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    ts = TrainStep(model, lr=1e-3)
+    src = torch.from_numpy(z["src"]).to(DEV)
+    labels = torch.from_numpy(z["labels"]).to(DEV)
+    for bad in (labels.int(), labels[:-1], labels.cpu(), labels.float(), labels.view(-1, 1)):
+        with pytest.raises(ValueError):
+            ts.step(src, bad)
+    ts.step(src, labels)
+    loss, _ = ts.read_stats()
+    assert abs(loss - float(z["loss"])) < 1e-4
+    oob = labels.clone()
+    oob[0] = GOLDEN_CASES["vit_p16"][1]["num_classes"]
+    ts.step(src, oob)
+    with pytest.raises(RuntimeError, match="label outside"):
+        ts.read_stats()
+    neg = labels.clone()
+    neg[1] = -1
+    ts.step(src, neg)
+    with pytest.raises(RuntimeError, match="label outside"):
+        ts.read_stats()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_non_current_device():
+    """The reference's plain `.to(device)` usage: model and batch on cuda:1 while cuda:0 is the current device (ADVICE r1:
+    the ABI switches to the device that owns the buffers)."""
+    z, params, grads, _ = load_golden("vit_p16")
+    torch.cuda.set_device(0)
+    dev1 = torch.device("cuda", 1)
+    kind, kw = GOLDEN_CASES["vit_p16"]
+    model = amc.ViTAMCTransformer(**kw, drop_prob=0.0, device=dev1, compute_dtype="fp32")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    src = torch.from_numpy(z["src"]).to(dev1)
+    labels = torch.from_numpy(z["labels"]).to(dev1)
+    assert torch.cuda.current_device() == 0
+    ts = TrainStep(model, lr=1e-3)
+    ts.step(src, labels)
+    loss, _ = ts.read_stats()
+    assert abs(loss - float(z["loss"])) < 1e-4
+    assert torch.cuda.current_device() == 0

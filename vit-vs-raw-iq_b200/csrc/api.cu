@@ -697,6 +697,7 @@ int amc_model_workspace(const AmcDesc* desc, AmcWorkspaceInfo* out) {
 
 int amc_model_fwd(const AmcDesc* desc, const float* src, const float* params, const float* pos, void* workspace,
                   float* logits, float* enc_out, amc_stream_t stream) {
+  DeviceGuard dev_guard(params);
   AMC_CHECK_ARG(desc && params && pos, "NULL argument");
   AMC_CHECK_ARG(src || desc->B == 0, "src is NULL");
   cudaStream_t st = (cudaStream_t)stream;
@@ -712,6 +713,7 @@ int amc_model_fwd(const AmcDesc* desc, const float* src, const float* params, co
 
 int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, void* workspace, const float* dlogits,
                   const float* denc_out, float* grads, int stage_begin, int stage_end, amc_stream_t stream) {
+  DeviceGuard dev_guard(params);
   (void)src;
   AMC_CHECK_ARG(desc && params && grads, "NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -727,6 +729,7 @@ int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, vo
 
 int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float label_smoothing, float grad_scale,
                 float loss_scale, float* dlogits, float* stats, amc_stream_t stream) {
+  DeviceGuard dev_guard(logits);
   AMC_CHECK_ARG(B >= 0 && C >= 1 && logits && labels, "bad argument");
   ProfScope ps("ce_loss", (cudaStream_t)stream);
   return ce_loss(B, C, logits, labels, label_smoothing, grad_scale, loss_scale, dlogits, stats, (cudaStream_t)stream);
@@ -735,6 +738,7 @@ int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float 
 int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float lr,
                         float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                         int64_t step, float* norm_ws, amc_stream_t stream) {
+  DeviceGuard dev_guard(params);
   AMC_CHECK_ARG(n >= 0 && params && grads && exp_avg && exp_avg_sq && norm_ws, "bad argument");
   ProfScope ps("adamw_clip", (cudaStream_t)stream, 0.0, (double)n * 32);
   return adamw_clip(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale,
@@ -742,6 +746,7 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
 }
 
 int amc_iq_stats(int64_t n_frames, int64_t frame_len, const float* x, double* acc4, amc_stream_t stream) {
+  DeviceGuard dev_guard(x);
   AMC_CHECK_ARG(n_frames >= 0 && frame_len >= 1 && x && acc4, "bad argument");
   AMC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7) == 0, "frames must be 8-byte aligned");
   return iq_stats(n_frames * frame_len, x, acc4, (cudaStream_t)stream);
@@ -750,6 +755,7 @@ int amc_iq_stats(int64_t n_frames, int64_t frame_len, const float* x, double* ac
 int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA, const void* B, int ldb, int transB,
              const float* bias, const float* res32, int ldres, int relu, void* D16, int ldd16, float* D32, int ldd32,
              int accumulate, amc_stream_t stream) {
+  DeviceGuard dev_guard(A);
   AMC_CHECK_ARG(A && B && (D16 || D32), "NULL argument");
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.transA = transA; g.B = B; g.ldb = ldb; g.transB = transB;
@@ -764,6 +770,7 @@ int amc_gemm(int dtype, int M, int N, int K, const void* A, int lda, int transA,
 int amc_gemm_ln(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
                 const float* res32, const float* gamma, const float* beta, float eps, void* y16, float* y32,
                 void* xhat, float* rstd, amc_stream_t stream) {
+  DeviceGuard dev_guard(A);
   AMC_CHECK_ARG(A && B && res32 && gamma && beta && y16 && y32, "NULL argument");
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb;
@@ -775,6 +782,7 @@ int amc_gemm_ln(int M, int N, int K, const void* A, int lda, const void* B, int 
 
 int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const void* mask,
                        float mask_scale, void* D16, amc_stream_t stream) {
+  DeviceGuard dev_guard(A);
   AMC_CHECK_ARG(A && B && mask && D16, "NULL argument");
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb;
@@ -784,12 +792,14 @@ int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* 
 
 int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, float* lse,
                       amc_stream_t stream) {
+  DeviceGuard dev_guard(qkv);
   AMC_CHECK_ARG(qkv && out, "NULL argument");
   if (dtype == AMC_BF16)
     return attention_fwd<bf16>(B, T, h, dh, (const bf16*)qkv, (bf16*)out, lse, (cudaStream_t)stream);
   return attention_fwd<float>(B, T, h, dh, (const float*)qkv, (float*)out, lse, (cudaStream_t)stream);
 }
 int amc_attention_cls_fwd(int B, int T, int h, int dh, const void* qkv, void* out, amc_stream_t stream) {
+  DeviceGuard dev_guard(qkv);
   AMC_CHECK_ARG(qkv && out, "NULL argument");
   AMC_CHECK_ARG((h * dh) % 8 == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "attention_cls: rows must be 16-byte aligned");
@@ -797,6 +807,7 @@ int amc_attention_cls_fwd(int B, int T, int h, int dh, const void* qkv, void* ou
 }
 int amc_attention_cls_bwd(int B, int T, int h, int dh, const void* qkv, const void* dout, void* dqkv, float* dbias,
                           amc_stream_t stream) {
+  DeviceGuard dev_guard(qkv);
   AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
   AMC_CHECK_ARG((h * dh) % 8 == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) |
                                        reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
@@ -805,6 +816,7 @@ int amc_attention_cls_bwd(int B, int T, int h, int dh, const void* qkv, const vo
 }
 int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, const void* out, const float* lse,
                       const void* dout, void* dqkv, float* dbias, amc_stream_t stream) {
+  DeviceGuard dev_guard(qkv);
   AMC_CHECK_ARG(qkv && dout && dqkv, "NULL argument");
   if (dtype == AMC_BF16)
     return attention_bwd<bf16>(B, T, h, dh, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)dout, (bf16*)dqkv, dbias,
@@ -815,6 +827,7 @@ int amc_attention_bwd(int dtype, int B, int T, int h, int dh, const void* qkv, c
 
 int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamma, const float* beta, float eps,
                       void* y16, float* y32, void* xhat, float* rstd, amc_stream_t stream) {
+  DeviceGuard dev_guard(u);
   AMC_CHECK_ARG(u && gamma && beta, "NULL argument");
   if (dtype == AMC_BF16)
     return ln_fwd<bf16>(M, d, u, gamma, beta, eps, (bf16*)y16, y32, (bf16*)xhat, rstd, (cudaStream_t)stream);
@@ -822,6 +835,7 @@ int amc_layernorm_fwd(int dtype, int M, int d, const float* u, const float* gamm
 }
 int amc_layernorm_bwd(int dtype, int M, int d, const float* dy, const void* xhat, const float* rstd,
                       const float* gamma, void* du16, float* du32, float* dgamma, float* dbeta, amc_stream_t stream) {
+  DeviceGuard dev_guard(dy);
   AMC_CHECK_ARG(dy && xhat && rstd && gamma, "NULL argument");
   DropoutCfg nodrop = make_dropout(0.f, 0, 0, false);
   if (dtype == AMC_BF16)
@@ -833,6 +847,7 @@ int amc_layernorm_bwd(int dtype, int M, int d, const float* dy, const void* xhat
 
 int amc_frontend_fwd(const AmcDesc* desc, const float* src, const float* emb_w, const float* emb_b, const float* cls,
                      const float* pos, void* scratch, size_t scratch_bytes, float* x0, amc_stream_t stream) {
+  DeviceGuard dev_guard(src);
   AMC_CHECK_ARG(desc && src && emb_w && emb_b && pos && x0, "NULL argument");
   AMC_CHECK_ARG(desc->dtype == AMC_F32, "amc_frontend_fwd operator call is fp32-only; use amc_model_fwd for bf16");
   Dims m;

@@ -435,16 +435,7 @@ int make_map3(CUtensorMap* map, const void* base, int B, int T, int cols, int dh
   return 0;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return device_sm_count(); }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 

@@ -136,6 +136,42 @@ __host__ __device__ __forceinline__ uint32_t site_attn(int l) { return 1 + 3 * l
 __host__ __device__ __forceinline__ uint32_t site_hidden(int l) { return 2 + 3 * l; }
 __host__ __device__ __forceinline__ uint32_t site_ffn(int l) { return 3 + 3 * l; }
 
+// Every entry point runs on the device that owns its buffers, whatever the caller's current device is (a model on
+// cuda:1 while cuda:0 is current is plain `.to(device)` usage in the reference): kernels, cudaFuncSetAttribute and tensor-
+// map encoding all act on the CURRENT device, so the ABI switches to the buffers' device for the call and back.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes a;
+    if (device_ptr != nullptr && cudaPointerGetAttributes(&a, device_ptr) == cudaSuccess &&
+        (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) {
+      int cur = 0;
+      if (cudaGetDevice(&cur) == cudaSuccess && cur != a.device && cudaSetDevice(a.device) == cudaSuccess) prev = cur;
+    } else {
+      (void)cudaGetLastError();        // a host pointer is an argument error the callee reports; clear the sticky code
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// SM count of the current device (cached per device)
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

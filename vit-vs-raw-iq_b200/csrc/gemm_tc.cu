@@ -708,16 +708,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int
   return make_map_ex(map, base, rows, cols, ld, box_cols, box_rows, false, false);
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_sm_count(); }
 
 template <int BN, int MODE_MN, int CS = 0>
 int launch(const GemmArgs& g, cudaStream_t st) {

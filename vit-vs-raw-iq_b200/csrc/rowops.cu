@@ -601,7 +601,11 @@ __global__ void ce_loss_kernel(int B, int C, const float* __restrict__ logits, c
     float se = 0.f;
     for (int k = 0; k < C; ++k) se += expf(z[k] - mx);
     const float lse = logf(se);
-    const int y = (int)labels[b];
+    const int64_t y64 = labels[b];
+    const int y = (int)y64;
+    // nn.CrossEntropyLoss raises on a target outside [0, C); an asynchronous kernel cannot, so the frame's loss becomes
+    // NaN: the running loss statistic is NaN from then on and the host raises when it reads it (trainer.read_stats)
+    const float poison = (y64 < 0 || y64 >= (int64_t)C) ? __int_as_float(0x7fc00000) : 0.f;
     float sum_logp = 0.f;
     for (int k = 0; k < C; ++k) {
       const float logp = z[k] - mx - lse;
@@ -611,6 +615,7 @@ __global__ void ce_loss_kernel(int B, int C, const float* __restrict__ logits, c
       if (k == y) loss -= (1.f - ls) * logp;
     }
     loss -= ls / (float)C * sum_logp;
+    loss += poison;
     correct = (am == y) ? 1.f : 0.f;
   }
   loss = warp_sum(loss);

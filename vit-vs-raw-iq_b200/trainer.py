@@ -85,6 +85,15 @@ class TrainStep:
         self.model.train()
         desc = core.make_desc(src, training=True, module_training=True)
         B = desc.B
+        # the kernel reads `labels` as B contiguous int64 on the model's device: anything else is an out-of-bounds or
+        # garbage device read (nn.CrossEntropyLoss raises in these cases too)
+        if not (isinstance(labels, torch.Tensor) and labels.is_cuda and labels.device == self.dev):
+            raise ValueError(f"labels must be a CUDA tensor on {self.dev}")
+        if labels.dtype != torch.int64 or labels.dim() != 1 or labels.numel() != B or not labels.is_contiguous():
+            raise ValueError(f"labels must be a contiguous int64 tensor of shape [{B}], got {labels.dtype} "
+                             f"{tuple(labels.shape)}")
+        if src.device != self.dev:
+            raise ValueError(f"src is on {src.device}, the model on {self.dev}")
         ws, logits, dlogits = self._buffers(B, desc)
         flat = self.model.flat_parameters()
         st = torch.cuda.current_stream(self.dev).cuda_stream
@@ -120,7 +129,16 @@ class TrainStep:
         if reset:
             self.stats.zero_()
             self.frames_seen = 0
+        _check_loss(s[0])
         return s[0] / n, s[1] / n
+
+
+def _check_loss(loss_sum: float) -> None:
+    """amc_ce_loss turns a frame's loss into NaN when its label is outside [0, num_classes) -- the case in which
+    nn.CrossEntropyLoss raises (R/training/train.py:260); a diverged model shows up here the same way."""
+    if loss_sum != loss_sum:
+        raise RuntimeError("training loss is NaN: a label outside [0, num_classes) (nn.CrossEntropyLoss would have "
+                           "raised 'Target out of bounds') or a diverged model")
 
 
 class HostPipeline:
@@ -164,6 +182,7 @@ class HostPipeline:
         prev = None
         if self.i > 0:
             self.loss_evt[1 - k].synchronize()
+            _check_loss(float(self.loss_host[1 - k][0]))
             prev = float(self.loss_host[1 - k][0]) / self.batch
         self.i += 1
         return prev
@@ -173,6 +192,7 @@ class HostPipeline:
             return None
         k = (self.i - 1) & 1
         self.loss_evt[k].synchronize()
+        _check_loss(float(self.loss_host[k][0]))
         return float(self.loss_host[k][0]) / self.batch
 
 
