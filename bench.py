@@ -294,6 +294,8 @@ def main():
                     help="also time the reference port in PyTorch eager on the GPU (reported beside; off by default: the "
                          "default run touches oracle/ only for the CPU baseline)")
     ap.add_argument("--no-gpu-eager", action="store_true", help=argparse.SUPPRESS)   # accepted, now the default
+    ap.add_argument("--graph", action="store_true",
+                    help="single GPU: drive the step as one CUDA-graph replay (GraphTrainStep) -- the launch-bound small batches")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -308,7 +310,7 @@ def main():
     import torch.distributed as dist
     import vit_vs_raw_iq_b200 as amc
     from vit_vs_raw_iq_b200 import _lib, synth
-    from vit_vs_raw_iq_b200.trainer import HostPipeline, HostPredictor, TrainStep, predict
+    from vit_vs_raw_iq_b200.trainer import GraphTrainStep, HostPipeline, HostPredictor, TrainStep, predict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -346,8 +348,9 @@ def main():
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
-    trainer = TrainStep(model, lr=w["lr"], weight_decay=w["wd"], betas=(0.9, 0.99), max_norm=1.0,
-                        label_smoothing=0.1)
+    step_cls = GraphTrainStep if (args.graph and world == 1) else TrainStep
+    trainer = step_cls(model, lr=w["lr"], weight_decay=w["wd"], betas=(0.9, 0.99), max_norm=1.0,
+                       label_smoothing=0.1)
 
     def barrier():
         if world > 1:
@@ -377,8 +380,11 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _lib.lib.amc_launch_count()
+    replays0 = getattr(trainer, "replays", 0)
     ms_train = timed(lambda i: trainer.step(dev_x[i % n_batches], dev_y[i % n_batches]), args.steps)
     launches = _lib.lib.amc_launch_count() - launches0
+    if step_cls is GraphTrainStep:      # kernels of the library launched by the graph replays of the timed region
+        launches += (trainer.replays - replays0) * trainer.kernels_per_replay
     loss, acc = trainer.read_stats()
 
     # ---- end to end from host buffers (e2e) -----------------------------------------------------------
@@ -414,8 +420,8 @@ def main():
     # ---- in-situ kernel-class timing for the roofline --------------------------------------------------
     _lib.profile(True)
     prof_steps = 3
-    for i in range(prof_steps):
-        trainer.step(dev_x[i % n_batches], dev_y[i % n_batches])
+    for i in range(prof_steps):            # (the in-library events need real launches: graph mode runs these steps eagerly)
+        (trainer._run if step_cls is GraphTrainStep else trainer.step)(dev_x[i % n_batches], dev_y[i % n_batches])
     prof = _lib.profile_dump()
     _lib.profile(False)
 
@@ -478,6 +484,7 @@ def main():
         "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "global_batch": frames, "tokens": T,
                    **{k: kw[k] for k in ("d_model", "n_head", "n_layers", "ffn_hidden", "num_classes", "drop_prob")},
                    "parallelism": f"dp{world}", "optimizer": "clip1.0+AdamW", "label_smoothing": 0.1,
+                   "step_driver": "cuda_graph_replay" if step_cls is GraphTrainStep else "stream_launches",
                    "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; 3 batches rotate",
                    "input": f"raw [B,{X.shape[1]},2] fp32 frames, z-score+framing fused in the front end"},
         "model_tflops": train_fps * 3 * fl_frame / 1e12,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AMC_ABI_VERSION 4
+#define AMC_ABI_VERSION 5
 
 enum { AMC_KIND_RAWIQ = 0, AMC_KIND_VIT = 1 };
 enum { AMC_F32 = 0, AMC_BF16 = 1 };
@@ -71,6 +71,9 @@ typedef struct AmcDesc {
   float   norm[4];       /* i_mean, i_std, q_mean, q_std for AMC_INPUT_RAW */
   uint64_t seed;         /* dropout: counter-based RNG key */
   uint64_t offset;       /* dropout: per-step counter */
+  const uint32_t* step_counter;  /* device memory or NULL: its value is added to `offset` on the device, so one captured
+                                    CUDA graph of a training step draws fresh masks on every replay (the counter is advanced by
+                                    amc_adamw_clip_step_graph) */
 } AmcDesc;
 
 /* Offsets (in floats) of every parameter inside the flat fp32 parameter blob.  The same
@@ -142,6 +145,15 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
                         float lr, float beta1, float beta2, float eps, float weight_decay,
                         float max_norm, float grad_scale, int64_t step, float* norm_ws,
                         amc_stream_t stream);
+
+/* The same update with the step number kept on the DEVICE: step = *step_counter + 1 is read by the kernels (AdamW bias
+ * corrections) and the counter is incremented at the end, so the call -- and the whole training step around it -- can be
+ * captured once in a CUDA graph and replayed (R/training/train.py:258-271 at the reference's batch of 256 frames is
+ * launch-bound otherwise). */
+int amc_adamw_clip_step_graph(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                              float lr, float beta1, float beta2, float eps, float weight_decay,
+                              float max_norm, float grad_scale, uint32_t* step_counter, float* norm_ws,
+                              amc_stream_t stream);
 
 /* Dataset-level normalisation statistics on the device (R/dataloader/dataset.py:115-157): for interleaved
  * frames x [n_frames, frame_len, 2] fp32, acc4 (device, fp64, zeroed by the caller) += {sum I, sum I^2, sum Q,

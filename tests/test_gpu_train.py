@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 from conftest import GOLDEN_CASES, GOLDEN_HP, load_golden  # noqa: E402
 
 import vit_vs_raw_iq_b200 as amc  # noqa: E402
-from vit_vs_raw_iq_b200.trainer import HostPipeline, TrainStep, predict  # noqa: E402
+from vit_vs_raw_iq_b200.trainer import GraphTrainStep, HostPipeline, TrainStep, predict  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -298,3 +298,45 @@ def test_model_on_a_non_current_device():
     loss, _ = ts.read_stats()
     assert abs(loss - float(z["loss"])) < 1e-4
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("name,dtype", [("rawiq_seg16", "fp32"), ("vit_p16", "bf16")])
+def test_graph_train_step_matches_the_eager_step(name, dtype):
+    """GraphTrainStep (one CUDA-graph replay per step, step number and dropout counter on the device) follows TrainStep:
+    with dropout off the parameters after 6 steps agree to fp32 round-off (the weight-gradient atomics reorder sums)."""
+    z, params, _, _ = load_golden(name)
+    src = torch.from_numpy(z["src"]).to(DEV)
+    labels = torch.from_numpy(z["labels"]).to(DEV)
+    outs = []
+    for cls in (TrainStep, GraphTrainStep):
+        model = build(name, dtype)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+        ts = cls(model, lr=1e-3, weight_decay=1e-2)
+        losses = []
+        for _ in range(6):
+            ts.step(src, labels)
+            losses.append(ts.read_stats()[0])
+        outs.append((model.flat_parameters().clone(), losses))
+        if cls is GraphTrainStep:
+            assert ts._graph is not None and int(ts.counter.item()) == 6
+    (p0, l0), (p1, l1) = outs
+    tol = 2e-5 if dtype == "fp32" else 2e-2
+    assert (p0 - p1).abs().max().item() <= tol * p0.abs().max().item()
+    assert all(abs(a - b) <= 5e-3 * abs(a) + 1e-5 for a, b in zip(l0, l1)), (l0, l1)
+    assert l0[-1] < l0[0]
+
+
+def test_graph_train_step_draws_new_dropout_masks_every_replay():
+    """The dropout counter lives in device memory, so replays of one captured graph use different masks: with lr = 0 the
+    weights never move, yet the training loss of the same batch changes from step to step (and repeats nowhere)."""
+    z, params, _, _ = load_golden("vit_p16")
+    model = build("vit_p16", "fp32", drop=0.3)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    ts = GraphTrainStep(model, lr=0.0, weight_decay=0.0)
+    src = torch.from_numpy(z["src"]).to(DEV)
+    labels = torch.from_numpy(z["labels"]).to(DEV)
+    losses = []
+    for _ in range(6):
+        ts.step(src, labels)
+        losses.append(round(ts.read_stats()[0], 6))
+    assert len(set(losses)) == len(losses), losses

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libamc_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 KIND_RAWIQ, KIND_VIT = 0, 1
 F32, BF16 = 0, 1
 INPUT_MODEL, INPUT_RAW = 0, 1
@@ -25,7 +25,7 @@ class AmcDesc(C.Structure):
         ("seq_len", C.c_int32), ("seg", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
         ("patch", C.c_int32), ("has_cls", C.c_int32), ("head_ln", C.c_int32), ("input_layout", C.c_int32),
         ("training", C.c_int32), ("p_drop", C.c_float), ("ln_eps", C.c_float), ("head_ln_eps", C.c_float),
-        ("norm", C.c_float * 4), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("norm", C.c_float * 4), ("seed", C.c_uint64), ("offset", C.c_uint64), ("step_counter", C.c_void_p),
     ]
 
 
@@ -61,6 +61,7 @@ def _load():
         "amc_model_bwd": [C.POINTER(AmcDesc), vp, vp, vp, vp, vp, vp, i32, i32, vp],
         "amc_ce_loss": [i32, i32, vp, vp, f32, f32, f32, vp, vp, vp],
         "amc_adamw_clip_step": [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, i64, vp, vp],
+        "amc_adamw_clip_step_graph": [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp],
         "amc_iq_stats": [i64, i64, vp, vp, vp],
         "amc_gemm": [i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, vp, i32, i32, vp],
         "amc_gemm_ln": [i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],

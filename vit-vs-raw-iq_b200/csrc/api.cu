@@ -278,7 +278,7 @@ struct Model {
     AMC_CHECK_ARG(workspace != nullptr || m.B == 0, "workspace is NULL");
     AMC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
     carve<E>(D, m, L, (char*)workspace, w);
-    drop = make_dropout(D.p_drop, D.seed, D.offset, true);
+    drop = make_dropout(D.p_drop, D.seed, D.offset, true, D.step_counter);
     return 0;
   }
   // fp32 parameter inside the blob
@@ -743,6 +743,16 @@ int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, 
   ProfScope ps("adamw_clip", (cudaStream_t)stream, 0.0, (double)n * 32);
   return adamw_clip(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale,
                     step, norm_ws, (cudaStream_t)stream);
+}
+
+int amc_adamw_clip_step_graph(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                              uint32_t* step_counter, float* norm_ws, amc_stream_t stream) {
+  DeviceGuard dev_guard(params);
+  AMC_CHECK_ARG(n >= 0 && params && grads && exp_avg && exp_avg_sq && norm_ws && step_counter, "bad argument");
+  ProfScope ps("adamw_clip", (cudaStream_t)stream, 0.0, (double)n * 32);
+  return adamw_clip_dev(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale,
+                        step_counter, norm_ws, (cudaStream_t)stream);
 }
 
 int amc_iq_stats(int64_t n_frames, int64_t frame_len, const float* x, double* acc4, amc_stream_t stream) {

@@ -91,9 +91,11 @@ struct DropoutCfg {
   uint32_t thresh;  // keep iff rnd >= thresh, thresh = p * 2^32
   uint32_t seed_lo, seed_hi;
   uint32_t off_lo, off_hi;
+  const uint32_t* ctr;   // device step counter added to the offset (CUDA-graph replays), or nullptr
 };
-inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool training) {
+inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool training, const uint32_t* ctr = nullptr) {
   DropoutCfg c;
+  c.ctr = ctr;
   c.p = (training && p > 0.f) ? p : 0.f;
   c.scale = c.p > 0.f ? 1.f / (1.f - c.p) : 1.f;
   double t = (double)c.p * 4294967296.0;
@@ -114,7 +116,8 @@ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool tra
 // Dropout only needs an unbiased, well-mixed keep decision per element; it is not a cryptographic stream.
 // keep-multipliers (0 or scale) for elements [4*q4, 4*q4+4) of dropout site `site`
 __device__ __forceinline__ float4 dropout_mult4(const DropoutCfg& c, uint32_t site, uint64_t q4) {
-  const uint32_t key = c.seed_lo ^ (c.off_lo * 0x9E3779B9u) ^ (site * 0x85EBCA6Bu) ^ (c.seed_hi * 0x27D4EB2Fu) ^
+  const uint32_t off = c.off_lo + (c.ctr != nullptr ? __ldg(c.ctr) : 0u);
+  const uint32_t key = c.seed_lo ^ (off * 0x9E3779B9u) ^ (site * 0x85EBCA6Bu) ^ (c.seed_hi * 0x27D4EB2Fu) ^
                        (c.off_hi * 0x165667B1u);                                        // loop-invariant
   uint32_t h = (uint32_t)q4 * 0x9E3779B1u + ((uint32_t)(q4 >> 32) * 0x7FEB352Du + key);
   h ^= h >> 16;                                   // murmur3 finaliser: keys that differ in one bit (seed, step, site)

@@ -15,7 +15,7 @@ struct Epi {
   float mask_scale = 1.f;
   const float* pos = nullptr;     // [map_T, N] positional encoding (front end)
   int map_Ttok = 0, map_T = 0, map_cls = 0;  // front end: out_row = (m / Ttok) * T + cls + m % Ttok
-  DropoutCfg drop = {0.f, 1.f, 0u, 0u, 0u, 0u, 0u};
+  DropoutCfg drop = {0.f, 1.f, 0u, 0u, 0u, 0u, 0u, nullptr};
   uint32_t drop_site = 0;
   const float* res32 = nullptr;   // [M, ldres] fp32 residual / skip gradient
   int ldres = 0;

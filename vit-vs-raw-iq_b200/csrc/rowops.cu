@@ -707,6 +707,41 @@ __global__ void __launch_bounds__(256) adamw_kernel(int64_t n, float* __restrict
   }
 }
 
+// the same update with the step number read from device memory (CUDA-graph replays): bias corrections per block
+__global__ void __launch_bounds__(256) adamw_dev_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, float lr,
+                                                        float b1, float b2, float eps, float wd, float max_norm,
+                                                        float grad_scale, const uint32_t* __restrict__ step_counter,
+                                                        float* __restrict__ ws) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double step = (double)(*step_counter) + 1.0;
+    s_bc[0] = 1.f - (float)pow((double)b1, step);
+    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, step));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  float coef = grad_scale;
+  if (max_norm > 0.f) {
+    const float norm = sqrtf(ws[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws[1] = norm;
+    coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+__global__ void counter_inc_kernel(uint32_t* c) { *c += 1u; }
+
 // ---------------------------------------------------------------------------------------
 // Dataset normalisation statistics (R/dataloader/dataset.py:115-157): sums and sums of squares of the I and Q
 // channels of interleaved frames, fp64 accumulation, one atomic per block.  acc = {sum I, sum I^2, sum Q, sum Q^2}
@@ -954,6 +989,23 @@ int transpose_batch(TransposeBatch& tb, cudaStream_t st) {
   }
   if (tiles == 0) return 0;
   transpose_batch_kernel<<<tiles, 256, 0, st>>>(tb);
+  AMC_LAUNCH_CHECK();
+  return 0;
+}
+
+int adamw_clip_dev(int64_t n, float* p, float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
+                   float max_norm, float grad_scale, uint32_t* step_counter, float* ws, cudaStream_t st) {
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  if (n > 0) {
+    if (max_norm > 0.f) {
+      AMC_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(float), st));
+      sqnorm_kernel<<<blocks, 256, 0, st>>>(n, g, grad_scale, ws);
+      AMC_LAUNCH_CHECK();
+    }
+    adamw_dev_kernel<<<blocks, 256, 0, st>>>(n, p, g, m, v, lr, b1, b2, eps, wd, max_norm, grad_scale, step_counter, ws);
+    AMC_LAUNCH_CHECK();
+  }
+  counter_inc_kernel<<<1, 1, 0, st>>>(step_counter);
   AMC_LAUNCH_CHECK();
   return 0;
 }

@@ -46,6 +46,8 @@ int ce_loss(int B, int C, const float* logits, const int64_t* labels, float ls, 
 int cast_blob(int64_t n, const float* src, bf16* dst, cudaStream_t st);
 int transpose_batch(TransposeBatch& tb, cudaStream_t st);
 int iq_stats(int64_t n_pairs, const float* x, double* acc, cudaStream_t st);
+int adamw_clip_dev(int64_t n, float* p, float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
+                   float max_norm, float grad_scale, uint32_t* step_counter, float* ws, cudaStream_t st);
 int adamw_clip(int64_t n, float* p, float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
                float max_norm, float grad_scale, int64_t step, float* ws, cudaStream_t st);
 

@@ -218,7 +218,14 @@ class _Core:
         ns = getattr(self, "norm_stats", (0.0, 1.0, 0.0, 1.0))
         for i in range(4):
             d.norm[i] = ns[i]
-        d.seed, d.offset = getattr(self, "seed", 0), getattr(self, "calls", 0)
+        # dropout key: (seed, per-call counter); data-parallel ranks fold their rank in (TrainStep sets rank_salt) so that
+        # the shards do not share one mask
+        d.seed = (getattr(self, "seed", 0) ^ (getattr(self, "rank_salt", 0) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+        d.offset = getattr(self, "calls", 0)
+        ctr = getattr(self, "step_counter", None)          # device int32 tensor (CUDA-graph training): offset lives there
+        if ctr is not None:
+            d.offset = 0
+            d.step_counter = ctr.data_ptr()
         return d
 
     # ---- parameter blob ---------------------------------------------------------------------

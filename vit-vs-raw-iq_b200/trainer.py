@@ -42,6 +42,13 @@ class TrainStep:
         self.norm_ws = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.step_count = 0
         self.frames_seen = 0
+        if self.world > 1:
+            # replicas start identical whatever each rank's seed or checkpoint was (only gradients are reduced afterwards),
+            # and every rank draws its own dropout masks
+            for t in (flat.data, self.exp_avg, self.exp_avg_sq):
+                torch.distributed.broadcast(t, src=torch.distributed.get_global_rank(process_group, 0)
+                                            if process_group is not None else 0, group=process_group)
+            self.core.rank_salt = torch.distributed.get_rank(process_group)
         self._ws: Optional[torch.Tensor] = None
         self._ws_key = None
         self._logits = self._dlogits = None
@@ -139,6 +146,81 @@ def _check_loss(loss_sum: float) -> None:
     if loss_sum != loss_sum:
         raise RuntimeError("training loss is NaN: a label outside [0, num_classes) (nn.CrossEntropyLoss would have "
                            "raised 'Target out of bounds') or a diverged model")
+
+
+class GraphTrainStep(TrainStep):
+    """``TrainStep`` for a fixed batch shape as ONE CUDA-graph launch per step.
+
+    At the reference's own batch (256 frames, R/training/train.py:94) a step is ~110 kernels of a few microseconds each:
+    launch- and host-bound.  Everything in it is static for a fixed shape -- kernel parameters, tensor maps, workspace --
+    except two scalars that change every step: the AdamW step number (bias corrections) and the dropout counter.  Both
+    live in one device word here (``AmcDesc.step_counter`` / ``amc_adamw_clip_step_graph``), so the step is captured once
+    and replayed.  The first call runs eagerly (one-time set-up must not happen inside a capture), the second captures.
+    Single process only: data-parallel runs use ``TrainStep`` (its NCCL buckets overlap backward on their own stream)."""
+
+    def __init__(self, model: _AMCBase, *args, **kwargs):
+        super().__init__(model, *args, **kwargs)
+        if self.world > 1:
+            raise RuntimeError("GraphTrainStep is single-process; use TrainStep under torch.distributed")
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.core.step_counter = self.counter
+        self._graph = None
+        self._gkey = None
+        self._gsrc = self._glabels = None
+        self.kernels_per_replay = 0
+        self.replays = 0
+
+    def _run(self, src: torch.Tensor, labels: torch.Tensor) -> None:
+        core = self.core
+        desc = core.make_desc(src, training=True, module_training=True)
+        B = desc.B
+        ws, logits, dlogits = self._buffers(B, desc)
+        flat = self.model.flat_parameters()
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        lib = _lib.lib
+        self.grads.zero_()
+        _lib.check(lib.amc_model_fwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), core.pos_buffer().data_ptr(),
+                                     ws.data_ptr(), logits.data_ptr(), 0, st), "amc_model_fwd")
+        _lib.check(lib.amc_ce_loss(B, core.C, logits.data_ptr(), labels.data_ptr(), self.ls, 1.0 / B, 1.0,
+                                   dlogits.data_ptr(), self.stats.data_ptr(), st), "amc_ce_loss")
+        _lib.check(lib.amc_model_bwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), ws.data_ptr(), dlogits.data_ptr(),
+                                     0, self.grads.data_ptr(), 0, core.n_layers + 2, st), "amc_model_bwd")
+        _lib.check(lib.amc_adamw_clip_step_graph(flat.numel(), flat.data_ptr(), self.grads.data_ptr(),
+                                                 self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.lr,
+                                                 self.betas[0], self.betas[1], self.eps, self.wd, self.max_norm, 1.0,
+                                                 self.counter.data_ptr(), self.norm_ws.data_ptr(), st),
+                   "amc_adamw_clip_step_graph")
+
+    def step(self, src: torch.Tensor, labels: torch.Tensor) -> None:
+        self.model.train()
+        B = int(src.shape[0])
+        if not (isinstance(labels, torch.Tensor) and labels.is_cuda and labels.device == self.dev):
+            raise ValueError(f"labels must be a CUDA tensor on {self.dev}")
+        if labels.dtype != torch.int64 or labels.dim() != 1 or labels.numel() != B or not labels.is_contiguous():
+            raise ValueError(f"labels must be a contiguous int64 tensor of shape [{B}], got {labels.dtype} "
+                             f"{tuple(labels.shape)}")
+        key = (tuple(src.shape), src.dtype, self.core.compute_dtype, self.core.drop_prob > 0)
+        if self._gkey != key:                              # new shape: this call runs eagerly, the next one captures
+            self._graph, self._gkey = None, key
+            self._gsrc, self._glabels = torch.empty_like(src), torch.empty_like(labels)
+            self._gsrc.copy_(src)
+            self._glabels.copy_(labels)
+            self._run(self._gsrc, self._glabels)
+        else:
+            self._gsrc.copy_(src, non_blocking=True)
+            self._glabels.copy_(labels, non_blocking=True)
+            if self._graph is None:
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.lib.amc_launch_count()
+                with torch.cuda.graph(g):
+                    self._run(self._gsrc, self._glabels)
+                self.kernels_per_replay = _lib.lib.amc_launch_count() - n0    # library kernels inside one replay
+                self._graph = g
+            self._graph.replay()
+            self.replays += 1
+        self.step_count += 1
+        self.frames_seen += B
 
 
 class HostPipeline:
