@@ -287,6 +287,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: workload's)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total frames per step, split evenly over the GPUs (overrides --batch)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="frames per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,6 +323,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or w["batch"]
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        B = args.global_batch // world
     kw = dict(w["kw"])
     T, ttok, kemb = geometry(w)
 
@@ -480,7 +486,8 @@ def main():
     line = {
         "metric": "train_frames_per_sec", "value": train_fps, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": args.workload, "frames_per_gpu_per_step": B, "global_batch": frames, "tokens": T,
                    **{k: kw[k] for k in ("d_model", "n_head", "n_layers", "ffn_hidden", "num_classes", "drop_prob")},
                    "parallelism": f"dp{world}", "optimizer": "clip1.0+AdamW", "label_smoothing": 0.1,

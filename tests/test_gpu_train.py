@@ -320,7 +320,9 @@ def test_graph_train_step_matches_the_eager_step(name, dtype):
         if cls is GraphTrainStep:
             assert ts._graph is not None and int(ts.counter.item()) == 6
     (p0, l0), (p1, l1) = outs
-    tol = 2e-5 if dtype == "fp32" else 2e-2
+    # (Adam's first steps move every weight by ~lr whatever the gradient's size, so the split-K atomics' summation-order
+    # noise in tiny gradient entries shows up at a few 1e-5 of the weight scale after 6 steps of lr = 1e-3)
+    tol = 1e-4 if dtype == "fp32" else 2e-2
     assert (p0 - p1).abs().max().item() <= tol * p0.abs().max().item()
     assert all(abs(a - b) <= 5e-3 * abs(a) + 1e-5 for a, b in zip(l0, l1)), (l0, l1)
     assert l0[-1] < l0[0]

@@ -47,6 +47,37 @@ elif [ "$MODE" = sanitize ]; then
     echo "compute-sanitizer $TOOL rc=$?" | tee -a "$OUT/${TAG}_status.txt"
     tail -5 "$OUT/${TAG}_sanitizer_${TOOL}.log"
   done
+elif [ "$MODE" = scale ]; then
+  # multi-GPU evidence on one box: `gpurun --gpus N -- bash tools/gpu_round.sh scale r2 "1 2"` (N = the largest count listed).
+  # Per count: the raw-IQ SPS-2 and cfg-1 workloads at 1024 and 256 frames per GPU (BASELINE configs[2] / [0]), a strong-
+  # scaling line of the default workload (32768 frames in total), the DP parity check, and -- at 8 GPUs -- the tuner grid.
+  NS=${3:-"1 2"}
+  run_n() {   # N, out file, bench args...
+    local n=$1 out=$2; shift 2
+    if [ "$n" = 1 ]; then timeout 200 python bench.py --gpus 1 "$@" > "$out" 2>> "$OUT/${TAG}_scale.err"
+    else timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 \
+           --master-port $((29500 + n)) bench.py --gpus "$n" "$@" > "$out" 2>> "$OUT/${TAG}_scale.err"; fi
+    echo "scale n=$n $* rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  }
+  for N in $NS; do
+    for W in rawiq_sps2_seg8_d256_L6 rawiq_seg16_d128_L6; do
+      for B in 1024 256; do
+        run_n "$N" "$OUT/${TAG}_scale_${W}_B${B}_${N}gpu.json" --workload "$W" --batch "$B" --steps 20 --warmup 5 --no-cpu-baseline
+      done
+    done
+    run_n "$N" "$OUT/${TAG}_strong_vit_p16_G32768_${N}gpu.json" --global-batch 32768 --steps 20 --warmup 5 --no-cpu-baseline
+    if [ "$N" -gt 1 ]; then
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29600 + N)) \
+        tools/dp_check.py > "$OUT/${TAG}_dp_check_${N}gpu.log" 2>&1; echo "dp_check n=$N rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+      tail -2 "$OUT/${TAG}_dp_check_${N}gpu.log"
+    fi
+    if [ "$N" = 8 ]; then
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29700 \
+        -m vit_vs_raw_iq_b200.tuning --particles 16 --iters 2 > "$OUT/${TAG}_tuning_8gpu.log" 2>&1; echo "tuning x8 rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+      tail -3 "$OUT/${TAG}_tuning_8gpu.log"
+    fi
+  done
+  cat "$OUT/${TAG}_status.txt"
 elif [ "$MODE" = summarise ]; then
   cp "$OUT/${TAG}_bench_1gpu.json" "profiles/${TAG}_bench_1gpu.json"
   cp "$OUT/${TAG}_bench_reference_arm.json" "profiles/${TAG}_bench_reference_arm.json"

@@ -31,6 +31,6 @@ if len(sys.argv) > 1:
             res[name] = round(e0.elapsed_time(e1) * 100, 1)
         print(sys.argv[1], (B, T, h, dh), res, flush=True)
 else:
-    for a in [0, 31]:
+    for a in [0, 32, 64, 96, 128, 224]:
         subprocess.run([sys.executable, __file__, str(a)], env=dict(os.environ, AMC_TC5_ABLATE=str(a)))
     subprocess.run([sys.executable, __file__, "legacy"], env=dict(os.environ, AMC_ATTN_LEGACY="1"))

@@ -505,7 +505,8 @@ struct Tc5BwdGeom {
   int kbox_rows, kbox_n;
   int tile_bytes, stage_bytes, ps_bytes, hdr_bytes, nst, NC;
   float scale, sl2;
-  int ablate;      // kernel-study switches (AMC_TC5_ABLATE): 1 no dVdK MMAs, 2 no dQ MMAs, 4 no S/dP MMAs, 8 no P/dS stores, 16 no exp math
+  int ablate;      // kernel-study switches (AMC_TC5_ABLATE): 1 no dVdK MMAs, 2 no dQ MMAs, 4 no S/dP MMAs, 8 no P/dS stores, 16 no exp math,
+                   // 32 no dQ stores, 64 no dK / dV stores, 128 no bias sums
 };
 constexpr int BWD_THREADS = 352;       // 8 row warps | MMA issuer + TMA | leftover 0 | leftover 1
 
@@ -933,15 +934,15 @@ attn_tc5_bwd_kernel(const __grid_constant__ CUtensorMap mQKV, const __grid_const
     auto epilogue_store = [&](const uint32_t (&kv)[HC], const uint32_t (&dq)[HC]) {
       if (p_kv) {
         const int key = p_k0 + (q & 1) * 32 + lane;
-        if (key < T)
+        if (key < T && !(gm.ablate & 64))
           st_half(dqkv + ((size_t)p_b * T + key) * (3 * gm.d) + (q < 2 ? 2 * gm.d : gm.d) + p_hh * dh + hf * HC, kv);
         // (the k-bias gradient is exactly zero -- rows of dS sum to zero, SURVEY Appendix B -- so only dV is summed)
-        if (dbias != nullptr && q < 2) colsum_half(kv, key < T, dbias + 2 * gm.d + p_hh * dh + hf * HC);
+        if (dbias != nullptr && q < 2 && !(gm.ablate & 128)) colsum_half(kv, key < T, dbias + 2 * gm.d + p_hh * dh + hf * HC);
       }
       if (p_dq) {
         const int rg = p_t * 128 + row;
-        if (rg < T) st_half(dqkv + ((size_t)p_b * T + rg) * (3 * gm.d) + p_hh * dh + hf * HC, dq);
-        if (dbias != nullptr) colsum_half(dq, rg < T, dbias + p_hh * dh + hf * HC);
+        if (rg < T && !(gm.ablate & 32)) st_half(dqkv + ((size_t)p_b * T + rg) * (3 * gm.d) + p_hh * dh + hf * HC, dq);
+        if (dbias != nullptr && !(gm.ablate & 128)) colsum_half(dq, rg < T, dbias + p_hh * dh + hf * HC);
       }
     };
     auto load_lse = [&](int u, float (&l)[2]) {
