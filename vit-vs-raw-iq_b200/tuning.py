@@ -23,6 +23,8 @@ units, one all-reduce of the score vector, no data-path collective.
 from __future__ import annotations
 
 import math
+import os
+import sys
 from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -144,6 +146,8 @@ def fitness_function(X: np.ndarray, train_ds, val_ds, rawiq_cfg: Dict, vit_cfg: 
     if evaluate is None:
         def evaluate(p):
             hp = repair_params(p, rawiq_cfg, vit_cfg)
+            if os.environ.get("AMC_TUNING_VERBOSE"):
+                print(f"[tuning rank {os.environ.get('RANK', '0')}] {hp}", file=sys.stderr, flush=True)
             model = build_models(p, rawiq_cfg, vit_cfg)
             return fast_train(model, train_ds, val_ds, hp["lr"], hp["batch_size"], device)
     dist = torch.distributed
