@@ -466,8 +466,17 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # written by tools/ncu_summary.py from `ncu --set full`
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = tj.get(args.workload, {}).get(dom["kernel"], {}).get("dram_bytes_per_launch")
+        ent = tj.get(args.workload, {}).get(dom["kernel"], {})
+        traffic = ent.get("dram_bytes_per_launch")
+        cap_frames = ent.get("frames") or w["batch"]          # frames per launch of the ncu capture (default: the bench batch)
+        if traffic is not None and cap_frames != B:
+            traffic_note = f"ncu capture at {cap_frames} frames per launch, scaled by {B}/{cap_frames}"
+            traffic = traffic * B / cap_frames
+        elif traffic is not None:
+            traffic_note = f"ncu capture at this launch size ({ent.get('report')})"
     roofline = {k: dom[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
+    if traffic is not None:
+        roofline["traffic_source"] = traffic_note
     roofline.update(traffic=traffic, peak_source=peaks["source"] + (" (sustained)" if dom["bound"] == "tensor" else ""),
                     launches_per_step=dom["launches_per_step"], avg_launch_ms=dom["avg_launch_ms"],
                     share_of_step=dom["share_of_step"],

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AMC_ABI_VERSION 5
+#define AMC_ABI_VERSION 6
 
 enum { AMC_KIND_RAWIQ = 0, AMC_KIND_VIT = 1 };
 enum { AMC_F32 = 0, AMC_BF16 = 1 };
@@ -65,7 +65,8 @@ typedef struct AmcDesc {
   int32_t input_layout;  /* AMC_INPUT_* */
   int32_t training;      /* 1 = keep activations for amc_model_bwd */
   float   p_drop;        /* dropout probability applied in this call (encoder_layer.py:12,16; encoder.py:84);
-                            pass 0 for module.eval() */
+                            pass 0 for module.eval().  The keep test runs on 16-bit hash fields: the effective probability is
+                            floor(p * 65536) / 65536, survivors are scaled by 1 / (1 - that), and p < 2^-16 means no dropout */
   float   ln_eps;        /* 1e-12 (layers_norm.py:5) */
   float   head_ln_eps;   /* 1e-5  (nn.LayerNorm default) */
   float   norm[4];       /* i_mean, i_std, q_mean, q_std for AMC_INPUT_RAW */
@@ -137,6 +138,14 @@ int amc_model_bwd(const AmcDesc* desc, const float* src, const float* params, vo
 int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float label_smoothing,
                 float grad_scale, float loss_scale, float* dlogits, float* stats, amc_stream_t stream);
 
+/* Predicted class per frame: out[b] = index of the first maximum of logits[b, :] (R/training/utils.py:311-317
+ * `outputs.max(1)`; V/training/utils.py the same).  logits fp32 [B, C], out device int64 [B]. */
+int amc_argmax(int B, int C, const float* logits, int64_t* out, amc_stream_t stream);
+
+/* Zero `bytes` bytes of device memory on `stream` (optimizer.zero_grad() of R/training/train.py:258 for the flat gradient
+ * blob; a memset node when captured into a CUDA graph). */
+int amc_zero(void* p, size_t bytes, amc_stream_t stream);
+
 /* clip_grad_norm_(max_norm) + AdamW.step fused over the flat blobs (R/training/train.py:266-271,506-511).
  * grads are first multiplied by grad_scale (1/world_size after an all-reduce SUM).  norm_ws: >= 2 floats
  * of device scratch (zeroed by the call); norm_ws[1] holds the pre-clip global norm afterwards.
@@ -189,7 +198,8 @@ int amc_gemm_relu_mask(int M, int N, int K, const void* A, int lda, const void* 
  * (multi_head_attention.py:34-47 + scale_dot_product_attention.py:26-37; mask is always None). */
 /*   lse  (nullable, fp32 [B, h, T]): log2-domain softmax row statistics max*c + log2(sum), c = log2(e)/sqrt(dh);
  *        written by the forward when given (training) and read by the backward together with `out`.
- *   out / lse may be NULL in backward (P is then recomputed with its row statistics);
+ *   out / lse may be NULL in backward for T <= 288 (P is then recomputed with its row statistics by the SIMT kernels --
+ *        a convenience form, several times slower than the training path that passes them);
  *   dbias (nullable, fp32 [3d]): += column sums of dqkv = gradients of the q | k | v biases. */
 int amc_attention_fwd(int dtype, int B, int T, int h, int dh, const void* qkv, void* out, float* lse,
                       amc_stream_t stream);

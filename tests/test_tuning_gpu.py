@@ -43,3 +43,27 @@ def test_default_fitness_builds_trains_and_scores_each_particle():
     X = np.array([[1, 64, 4, 1, 128, 0.0, 1e-3, 32, 32], [0, 64, 4, 1, 128, 0.2, 5e-4, 16, 8]], dtype=np.float64)
     f = tuning.fitness_function(X, train, val, RAWIQ_CFG, VIT_CFG, DEV)
     assert f.shape == (2,) and np.all(f <= 0.0) and np.all(f >= -1.0)
+
+
+def test_rank_sharded_swarm_under_torchrun():
+    """`python -m vit_vs_raw_iq_b200.tuning` under torchrun: every rank trains DIFFERENT candidates, so TrainStep must not
+    issue the data-parallel broadcast / all-reduce (round 2: the 8-GPU run hung in exactly that broadcast).  Two gloo ranks
+    share the visible GPU(s), so this runs on a one-GPU box; the answer must equal the single-process search."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    from conftest import ROOT
+    args = ["-m", "vit_vs_raw_iq_b200.tuning", "--particles", "4", "--iters", "2", "--train-frames", "256", "--val-frames", "128"]
+    one = subprocess.run([sys.executable] + args, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert one.returncode == 0, one.stderr[-2000:]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(port)] + args, capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, AMC_TUNING_BACKEND="gloo"))
+    assert two.returncode == 0, (two.stdout + two.stderr)[-3000:]
+    last = lambda out: json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert last(one.stdout)["best_config"] == last(two.stdout)["best_config"]

@@ -28,12 +28,29 @@ if [ "$MODE" = collect ]; then
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
       --log-file "$OUT/${TAG}_launches_train.csv" python tools/one_step.py > "$OUT/${TAG}_ncu_launch.log" 2>&1
     echo "ncu launch list rc=$?" | tee -a "$OUT/${TAG}_status.txt"
-    timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
-      -o "$OUT/${TAG}_full_step" python tools/one_step.py --batch 8192 > "$OUT/${TAG}_ncu_full.log" 2>&1
+    # the dominant class (weight-gradient GEMM) at the bench batch first -- seconds; then the whole default step
+    timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off -f -k regex:gemm_tc_kernel -c 8 \
+      -o "$OUT/${TAG}_full_wgrad" python tools/one_step.py > "$OUT/${TAG}_ncu_full_wgrad.log" 2>&1
+    echo "ncu full wgrad rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+    # full capture of the default step: the GEMM / LayerNorm / front-end classes at the bench batch (attention is T = 9 here)
+    timeout 420 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
+      -o "$OUT/${TAG}_full_step" python tools/one_step.py ${NCU_BATCH:+--batch $NCU_BATCH} > "$OUT/${TAG}_ncu_full.log" 2>&1
     echo "ncu full rc=$?" | tee -a "$OUT/${TAG}_status.txt"
   else
     echo "one_step.py failed without ncu: no ncu passes" | tee -a "$OUT/${TAG}_status.txt"
   fi
+  # the tcgen05 attention kernels on the raw-IQ SPS-1 / SPS-2 shapes (T = 129 / 257): launch list of the step + full capture
+  # of the attention kernels only
+  for W in rawiq_sps1_seg8_d256_L6 rawiq_sps2_seg8_d256_L6; do
+    if timeout 120 python tools/one_step.py --workload $W > "$OUT/${TAG}_one_step_${W}.log" 2>&1; then
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+        --log-file "$OUT/${TAG}_launches_${W}.csv" python tools/one_step.py --workload $W > "$OUT/${TAG}_ncu_launch_${W}.log" 2>&1
+      echo "ncu launch list $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+      timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -f -k regex:attn_ \
+        -o "$OUT/${TAG}_full_attn_${W}" python tools/one_step.py --workload $W > "$OUT/${TAG}_ncu_full_${W}.log" 2>&1
+      echo "ncu full attention $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+    fi
+  done
   nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/${TAG}_nvidia_smi.csv" 2>&1
   cat "$OUT/${TAG}_status.txt"
 elif [ "$MODE" = sanitize ]; then
@@ -87,8 +104,16 @@ elif [ "$MODE" = summarise ]; then
   [ -s "$OUT/${TAG}_launches_train.csv" ] && cp "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.csv" && \
     python tools/ncu_summary.py launches "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.md" \
       --title "${TAG}: ncu launch list of one training step (tools/one_step.py, default workload)"
+  [ -s "$OUT/${TAG}_full_wgrad.ncu-rep" ] && \
+    python tools/ncu_summary.py full "$OUT/${TAG}_full_wgrad.ncu-rep" "profiles/${TAG}_ncu_full_wgrad.json"
   [ -s "$OUT/${TAG}_full_step.ncu-rep" ] && \
     python tools/ncu_summary.py full "$OUT/${TAG}_full_step.ncu-rep" "profiles/${TAG}_ncu_full_step.json"
+  for W in rawiq_sps1_seg8_d256_L6 rawiq_sps2_seg8_d256_L6; do
+    [ -s "$OUT/${TAG}_launches_${W}.csv" ] && python tools/ncu_summary.py launches "$OUT/${TAG}_launches_${W}.csv" \
+      "profiles/${TAG}_launches_train_${W}.md" --title "${TAG}: ncu launch list of one training step (tools/one_step.py --workload $W)"
+    [ -s "$OUT/${TAG}_full_attn_${W}.ncu-rep" ] && \
+      python tools/ncu_summary.py full "$OUT/${TAG}_full_attn_${W}.ncu-rep" "profiles/${TAG}_ncu_full_attn_${W}.json" --workload $W
+  done
   tail -3 "$OUT/${TAG}_pytest_gpu.log"
 else
   echo "usage: $0 collect|sanitize|summarise <tag>"; exit 2

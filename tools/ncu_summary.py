@@ -31,8 +31,8 @@ def short(name):
 CLASS_OF = [
     (r"gemm_tc_kernel<\d+, *1, *\d+>", "gemm_wgrad"),
     (r"ln_bwd_vec_kernel", "ln_bwd"),
-    (r"attn_(frames|mma|tile|tc)_bwd_kernel", "attn_bwd"),
-    (r"attn_(frames|mma|tile|tc)_fwd_kernel", "attn_fwd"),
+    (r"attn_(frames|mma|tile|tc|tc5)_bwd_kernel", "attn_bwd"),
+    (r"attn_(frames|mma|tile|tc|tc5)_fwd_kernel", "attn_fwd"),
     (r"attn_long(_mma)?_fwd_kernel", "attn_fwd"),
     (r"patchify", "patchify"),
     (r"adamw_kernel", "adamw_clip"),
@@ -86,7 +86,7 @@ ALT = {"sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_act
        "sm__inst_executed_pipe_uniform.sum": None}
 
 
-def full(rep, out, workload):
+def full(rep, out, workload, frames=0):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
@@ -126,7 +126,10 @@ def full(rep, out, workload):
     for k, d in res.items():
         for pat, cls in CLASS_OF:
             if re.search(pat, k) and "dram_bytes_per_launch" in d:
-                e = wl.setdefault(cls, {"dram_bytes_per_launch": 0.0, "launches": 0, "kernels": [], "report": os.path.basename(rep)})
+                if wl.get(cls, {}).get("report") != os.path.basename(rep):
+                    wl.pop(cls, None)           # a new capture replaces the class's entry (no mixing of rounds / batch sizes)
+                e = wl.setdefault(cls, {"dram_bytes_per_launch": 0.0, "launches": 0, "kernels": [], "report": os.path.basename(rep),
+                                        "frames": frames or None})
                 if k in e["kernels"]:
                     continue
                 tot = e["dram_bytes_per_launch"] * e["launches"] + d["dram_bytes_per_launch"] * d["launches"]
@@ -144,8 +147,9 @@ if __name__ == "__main__":
     ap.add_argument("out")
     ap.add_argument("--title", default="ncu launch list")
     ap.add_argument("--workload", default="vit_p16_d256_L6")
+    ap.add_argument("--batch", type=int, default=0, help="frames per launch of the capture (0 = the workload's bench batch)")
     a = ap.parse_args()
     if a.mode == "launches":
         launches(a.src, a.out, a.title)
     else:
-        full(a.src, a.out, a.workload)
+        full(a.src, a.out, a.workload, a.batch)

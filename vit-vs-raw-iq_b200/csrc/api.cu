@@ -735,6 +735,20 @@ int amc_ce_loss(int B, int C, const float* logits, const int64_t* labels, float 
   return ce_loss(B, C, logits, labels, label_smoothing, grad_scale, loss_scale, dlogits, stats, (cudaStream_t)stream);
 }
 
+int amc_argmax(int B, int C, const float* logits, int64_t* out, amc_stream_t stream) {
+  DeviceGuard dev_guard(logits);
+  AMC_CHECK_ARG(B >= 0 && C >= 1 && logits && out, "bad argument");
+  ProfScope ps("argmax", (cudaStream_t)stream);
+  return argmax_rows(B, C, logits, out, (cudaStream_t)stream);
+}
+
+int amc_zero(void* p, size_t bytes, amc_stream_t stream) {
+  DeviceGuard dev_guard(p);
+  AMC_CHECK_ARG(p != nullptr || bytes == 0, "bad argument");
+  if (bytes) AMC_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return 0;
+}
+
 int amc_adamw_clip_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float lr,
                         float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                         int64_t step, float* norm_ws, amc_stream_t stream) {

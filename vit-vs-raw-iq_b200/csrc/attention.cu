@@ -4,6 +4,18 @@
 // reference materialises [B,h,T,T] fp32: scale_dot_product_attention.py:26-37).
 // Backward recomputes P from Q,K (SURVEY Appendix B "what to save"): phase 1 is query-row parallel
 // (row statistics, dQ), phase 2 is key-row parallel (dK, dV) -- no atomics, deterministic.
+//
+// Dispatch (attention_fwd / attention_bwd below), first match wins; every branch is reachable and covered by
+// tests/test_gpu_ops.py (the shape lists there name the branch each case exercises):
+//   T > 288                                   attn_long.cu   flash-style tiles (conv1d embedding, T = 1025)
+//   bf16, T <= 16, dh in {16,32,64}           attn_mma_*     frames x heads packed per CTA (ViT p16: T = 9)
+//   bf16, 49 <= T <= 272, dh in {16,32,64}    attn_tc5.cu    tcgen05 / TMEM, where it is the faster kernel (T > 80 or dh = 64)
+//   bf16, 16 < T <= 288, dh in {16,32,64}     attn_tiles.cu  mma.sync tiles (backward: while its tiles fit, i.e. not dh = 64, T > 176)
+//   T <= 32, dh <= 32, h T <= 256             attn_frames_*  SIMT, several frames per CTA (fp32 parity path; bf16 odd head dims)
+//   anything else (T <= 288, dh <= 128)       attn_fwd/bwd_kernel  SIMT, one CTA per (frame, head): fp32, head dims 48 / 96 / 128,
+//                                             backward without the forward's out / lse
+// (Round 2 removed a fourth generation -- the bulk-copy mma.sync "attn_tc" kernels -- that only dh = 64, 177 <= T <= 215
+//  backward still reached; those shapes take the SIMT kernel now.)
 #include <cstdlib>
 
 #include "attention.cuh"
@@ -852,418 +864,10 @@ inline int mma_frames(int T, int h, int dh, bool bwd) {
 // resident CTAs per SM for a given dynamic shared-memory size (256 threads each)
 inline int mma_ctas_per_sm(size_t sm) { return (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (sm + 1024))); }
 
-// ---------------------------------------------------------------------------------------------
-// Tensor-core attention for 16 < T <= 288 tokens (bf16, head dim 16*KD): the general single-CTA kernel.
-// A CTA owns one (frame, group of G heads): the q|k|v row segments of those heads are contiguous in HBM
-// (G*dh elements per token row and segment), so staging is three bulk row copies per token.  Work items
-// are (head, 16-row tile): a warp keeps the whole score row block [16 x T] in accumulator fragments
-// (NB blocks of 16 keys), so softmax needs no online rescaling.  Backward is two-phase and atomic-free:
-//   phase 1 (query tiles): P, delta, dQ ; row statistics (max, 1/sum, delta) go to shared memory
-//   phase 2 (key tiles)  : recomputes S^T = K Q^T per 16-query block from those statistics and accumulates
-//                          dK = dS^T Q and dV = P^T dO -- the transposed products come straight out of
-//                          the swapped operand roles, no transpose through memory.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t addr_a2(uint32_t base, int pitch_b, int row0, int T, int col0, int lane) {
-  const int r = min(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, T - 1);
-  return base + r * pitch_b + (col0 + (lane >> 4) * 8) * 2;
-}
-__device__ __forceinline__ uint32_t addr_bk2(uint32_t base, int pitch_b, int row0, int T, int col0, int lane) {
-  const int r = min(row0 + (lane & 7) + (lane >> 4) * 8, T - 1);
-  return base + r * pitch_b + (col0 + ((lane >> 3) & 1) * 8) * 2;
-}
-
-struct TcGeom {
-  int T, h, G, gd, pitch;          // gd = G*dh elements per row segment; pitch = (gd + 8) elements
-  int units;                       // B * (h / G)
-};
-
-template <int KD, int NB>
-__global__ void __launch_bounds__(128) attn_tc_fwd_kernel(TcGeom gm, const bf16* __restrict__ qkv,
-                                                          bf16* __restrict__ out, float scale) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int dh = 16 * KD;
-  const int T = gm.T, d = gm.h * dh, ld = 3 * d, pitch = gm.pitch, pb = pitch * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  bf16* sQ = reinterpret_cast<bf16*>(smem_raw + 128);
-  bf16* sK = sQ + (size_t)T * pitch;
-  bf16* sV = sK + (size_t)T * pitch;
-  bf16* sO = sV + (size_t)T * pitch;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  const int g = lane >> 2, cb = (lane & 3) * 2;
-  const int ngrp = gm.h / gm.G, NQ = (T + 15) >> 4;
-  const uint32_t rowb = (uint32_t)(gm.gd * 2);
-  if (tid == 0) mbar_init1(bar);
-  __syncthreads();
-  uint32_t it = 0;
-  for (int u = blockIdx.x; u < gm.units; u += gridDim.x, ++it) {
-    const int b = u / ngrp, hg = u - b * ngrp;
-    const bf16* src = qkv + (size_t)b * T * ld + hg * gm.gd;
-    if (tid == 0) {
-      bulk_wait_read0();                               // previous unit's output rows have left sO
-      mbar_expect(bar, rowb * 3u * (uint32_t)T);
-      for (int r = 0; r < T; ++r) {
-        bulk_g2s(sQ + (size_t)r * pitch, src + (size_t)r * ld, rowb, bar);
-        bulk_g2s(sK + (size_t)r * pitch, src + (size_t)r * ld + d, rowb, bar);
-        bulk_g2s(sV + (size_t)r * pitch, src + (size_t)r * ld + 2 * d, rowb, bar);
-      }
-    }
-    mbar_wait_parity(bar, it & 1);
-    __syncthreads();
-    for (int item = warp; item < gm.G * NQ; item += nw) {
-      const int hh = item / NQ, qt = item - hh * NQ;
-      const uint32_t qb = smem_addr(sQ + hh * dh), kb = smem_addr(sK + hh * dh), vb = smem_addr(sV + hh * dh);
-      float c[2 * NB][4];
-#pragma unroll
-      for (int i = 0; i < 2 * NB; ++i) { c[i][0] = 0.f; c[i][1] = 0.f; c[i][2] = 0.f; c[i][3] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < KD; ++ks) {
-        uint32_t a[4];
-        ldsm_x4(a, addr_a2(qb, pb, qt * 16, T, ks * 16, lane));
-#pragma unroll
-        for (int kbk = 0; kbk < NB; ++kbk) {
-          if (kbk * 16 < T) {
-            uint32_t bfr[4];
-            ldsm_x4(bfr, addr_bk2(kb, pb, kbk * 16, T, ks * 16, lane));
-            mma_bf16(c[2 * kbk], a, bfr[0], bfr[1]);
-            mma_bf16(c[2 * kbk + 1], a, bfr[2], bfr[3]);
-          }
-        }
-      }
-      // softmax over the full row block
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 2 * NB; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool ok = nt * 8 + cb + e < T;
-          c[nt][e] = ok ? c[nt][e] * scale : -INFINITY;
-          c[nt][2 + e] = ok ? c[nt][2 + e] * scale : -INFINITY;
-          m0 = fmaxf(m0, c[nt][e]);
-          m1 = fmaxf(m1, c[nt][2 + e]);
-        }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 2 * NB; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          c[nt][e] = __expf(c[nt][e] - m0);
-          c[nt][2 + e] = __expf(c[nt][2 + e] - m1);
-          s0 += c[nt][e];
-          s1 += c[nt][2 + e];
-        }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      const float i0 = 1.f / s0, i1 = 1.f / s1;
-      float o[2 * KD][4];
-#pragma unroll
-      for (int i = 0; i < 2 * KD; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
-#pragma unroll
-      for (int kbk = 0; kbk < NB; ++kbk) {
-        if (kbk * 16 < T) {
-          uint32_t pa[4] = {pack2(c[2 * kbk][0] * i0, c[2 * kbk][1] * i0), pack2(c[2 * kbk][2] * i1, c[2 * kbk][3] * i1),
-                            pack2(c[2 * kbk + 1][0] * i0, c[2 * kbk + 1][1] * i0),
-                            pack2(c[2 * kbk + 1][2] * i1, c[2 * kbk + 1][3] * i1)};
-#pragma unroll
-          for (int np = 0; np < KD; ++np) {
-            uint32_t bfr[4];
-            ldsm_x4_t(bfr, addr_a2(vb, pb, kbk * 16, T, np * 16, lane));
-            mma_bf16(o[2 * np], pa, bfr[0], bfr[1]);
-            mma_bf16(o[2 * np + 1], pa, bfr[2], bfr[3]);
-          }
-        }
-      }
-      const int r0 = qt * 16 + g, r1 = r0 + 8;
-      bf16* ob = sO + hh * dh + cb;
-#pragma unroll
-      for (int nt = 0; nt < 2 * KD; ++nt) {
-        if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * pitch + nt * 8) = pack2(o[nt][0], o[nt][1]);
-        if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * pitch + nt * 8) = pack2(o[nt][2], o[nt][3]);
-      }
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      bf16* dst = out + (size_t)b * T * d + hg * gm.gd;
-      for (int r = 0; r < T; ++r) bulk_s2g(dst + (size_t)r * d, sO + (size_t)r * pitch, rowb);
-      bulk_commit_group();
-    }
-  }
-  if (tid == 0) bulk_wait_all0();
-}
-
-template <int KD, int NB>
-__global__ void __launch_bounds__(128) attn_tc_bwd_kernel(TcGeom gm, const bf16* __restrict__ qkv,
-                                                          const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
-                                                          float scale) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int dh = 16 * KD;
-  const int T = gm.T, d = gm.h * dh, ld = 3 * d, pitch = gm.pitch, pb = pitch * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  bf16* sQ = reinterpret_cast<bf16*>(smem_raw + 128);
-  bf16* sK = sQ + (size_t)T * pitch;
-  bf16* sV = sK + (size_t)T * pitch;
-  bf16* sdO = sV + (size_t)T * pitch;
-  bf16* gQ = sdO + (size_t)T * pitch;                  // gradient staging: dQ | dK | dV
-  bf16* gK = gQ + (size_t)T * pitch;
-  bf16* gV = gK + (size_t)T * pitch;
-  float* st_m = reinterpret_cast<float*>(gV + (size_t)T * pitch);     // [G][T]
-  float* st_il = st_m + gm.G * T;
-  float* st_dl = st_il + gm.G * T;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  const int g = lane >> 2, cb = (lane & 3) * 2;
-  const int ngrp = gm.h / gm.G, NQ = (T + 15) >> 4;
-  const uint32_t rowb = (uint32_t)(gm.gd * 2);
-  if (tid == 0) mbar_init1(bar);
-  __syncthreads();
-  uint32_t it = 0;
-  for (int u = blockIdx.x; u < gm.units; u += gridDim.x, ++it) {
-    const int b = u / ngrp, hg = u - b * ngrp;
-    const bf16* src = qkv + (size_t)b * T * ld + hg * gm.gd;
-    const bf16* dsrc = dout + (size_t)b * T * d + hg * gm.gd;
-    if (tid == 0) {
-      bulk_wait_read0();                               // previous unit's gradient rows have left the staging tiles
-      mbar_expect(bar, rowb * 4u * (uint32_t)T);
-      for (int r = 0; r < T; ++r) {
-        bulk_g2s(sQ + (size_t)r * pitch, src + (size_t)r * ld, rowb, bar);
-        bulk_g2s(sK + (size_t)r * pitch, src + (size_t)r * ld + d, rowb, bar);
-        bulk_g2s(sV + (size_t)r * pitch, src + (size_t)r * ld + 2 * d, rowb, bar);
-        bulk_g2s(sdO + (size_t)r * pitch, dsrc + (size_t)r * d, rowb, bar);
-      }
-    }
-    mbar_wait_parity(bar, it & 1);
-    __syncthreads();
-    // ---------------- phase 1: query tiles -> statistics, dQ ----------------
-    for (int item = warp; item < gm.G * NQ; item += nw) {
-      const int hh = item / NQ, qt = item - hh * NQ;
-      const uint32_t qb = smem_addr(sQ + hh * dh), kb = smem_addr(sK + hh * dh), vb = smem_addr(sV + hh * dh),
-                     ob = smem_addr(sdO + hh * dh);
-      float c[2 * NB][4];
-#pragma unroll
-      for (int i = 0; i < 2 * NB; ++i) { c[i][0] = 0.f; c[i][1] = 0.f; c[i][2] = 0.f; c[i][3] = 0.f; }
-      uint32_t aq[KD][4], ao[KD][4];
-#pragma unroll
-      for (int ks = 0; ks < KD; ++ks) {
-        ldsm_x4(aq[ks], addr_a2(qb, pb, qt * 16, T, ks * 16, lane));
-        ldsm_x4(ao[ks], addr_a2(ob, pb, qt * 16, T, ks * 16, lane));
-      }
-#pragma unroll
-      for (int kbk = 0; kbk < NB; ++kbk) {
-        if (kbk * 16 < T) {
-#pragma unroll
-          for (int ks = 0; ks < KD; ++ks) {
-            uint32_t bfr[4];
-            ldsm_x4(bfr, addr_bk2(kb, pb, kbk * 16, T, ks * 16, lane));
-            mma_bf16(c[2 * kbk], aq[ks], bfr[0], bfr[1]);
-            mma_bf16(c[2 * kbk + 1], aq[ks], bfr[2], bfr[3]);
-          }
-        }
-      }
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 2 * NB; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool ok = nt * 8 + cb + e < T;
-          c[nt][e] = ok ? c[nt][e] * scale : -INFINITY;
-          c[nt][2 + e] = ok ? c[nt][2 + e] * scale : -INFINITY;
-          m0 = fmaxf(m0, c[nt][e]);
-          m1 = fmaxf(m1, c[nt][2 + e]);
-        }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 2 * NB; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          c[nt][e] = __expf(c[nt][e] - m0);
-          c[nt][2 + e] = __expf(c[nt][2 + e] - m1);
-          s0 += c[nt][e];
-          s1 += c[nt][2 + e];
-        }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      const float i0 = 1.f / s0, i1 = 1.f / s1;
-      // delta_i = sum_j P_ij dP_ij, dP = dO V^T computed block by block
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int kbk = 0; kbk < NB; ++kbk) {
-        if (kbk * 16 < T) {
-          float dp[2][4] = {};
-#pragma unroll
-          for (int ks = 0; ks < KD; ++ks) {
-            uint32_t bfr[4];
-            ldsm_x4(bfr, addr_bk2(vb, pb, kbk * 16, T, ks * 16, lane));
-            mma_bf16(dp[0], ao[ks], bfr[0], bfr[1]);
-            mma_bf16(dp[1], ao[ks], bfr[2], bfr[3]);
-          }
-#pragma unroll
-          for (int u2 = 0; u2 < 2; ++u2)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              d0 = fmaf(c[2 * kbk + u2][e] * i0, dp[u2][e], d0);
-              d1 = fmaf(c[2 * kbk + u2][2 + e] * i1, dp[u2][2 + e], d1);
-            }
-        }
-      }
-      d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-      d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-      const int r0 = qt * 16 + g, r1 = r0 + 8;
-      if ((lane & 3) == 0) {
-        if (r0 < T) { st_m[hh * T + r0] = m0; st_il[hh * T + r0] = i0; st_dl[hh * T + r0] = d0; }
-        if (r1 < T) { st_m[hh * T + r1] = m1; st_il[hh * T + r1] = i1; st_dl[hh * T + r1] = d1; }
-      }
-      // dQ = dS K, dS = P (dP - delta) scale   (dP recomputed block by block)
-      float dq[2 * KD][4];
-#pragma unroll
-      for (int i = 0; i < 2 * KD; ++i) { dq[i][0] = 0.f; dq[i][1] = 0.f; dq[i][2] = 0.f; dq[i][3] = 0.f; }
-#pragma unroll
-      for (int kbk = 0; kbk < NB; ++kbk) {
-        if (kbk * 16 < T) {
-          float dp[2][4] = {};
-#pragma unroll
-          for (int ks = 0; ks < KD; ++ks) {
-            uint32_t bfr[4];
-            ldsm_x4(bfr, addr_bk2(vb, pb, kbk * 16, T, ks * 16, lane));
-            mma_bf16(dp[0], ao[ks], bfr[0], bfr[1]);
-            mma_bf16(dp[1], ao[ks], bfr[2], bfr[3]);
-          }
-          uint32_t sa[4];
-          sa[0] = pack2(c[2 * kbk][0] * i0 * (dp[0][0] - d0) * scale, c[2 * kbk][1] * i0 * (dp[0][1] - d0) * scale);
-          sa[1] = pack2(c[2 * kbk][2] * i1 * (dp[0][2] - d1) * scale, c[2 * kbk][3] * i1 * (dp[0][3] - d1) * scale);
-          sa[2] = pack2(c[2 * kbk + 1][0] * i0 * (dp[1][0] - d0) * scale,
-                        c[2 * kbk + 1][1] * i0 * (dp[1][1] - d0) * scale);
-          sa[3] = pack2(c[2 * kbk + 1][2] * i1 * (dp[1][2] - d1) * scale,
-                        c[2 * kbk + 1][3] * i1 * (dp[1][3] - d1) * scale);
-#pragma unroll
-          for (int np = 0; np < KD; ++np) {
-            uint32_t bfr[4];
-            ldsm_x4_t(bfr, addr_a2(kb, pb, kbk * 16, T, np * 16, lane));     // B[k=key][n=c] = K[key][c]
-            mma_bf16(dq[2 * np], sa, bfr[0], bfr[1]);
-            mma_bf16(dq[2 * np + 1], sa, bfr[2], bfr[3]);
-          }
-        }
-      }
-      bf16* og = gQ + hh * dh + cb;
-#pragma unroll
-      for (int nt = 0; nt < 2 * KD; ++nt) {
-        if (r0 < T) *reinterpret_cast<uint32_t*>(og + (size_t)r0 * pitch + nt * 8) = pack2(dq[nt][0], dq[nt][1]);
-        if (r1 < T) *reinterpret_cast<uint32_t*>(og + (size_t)r1 * pitch + nt * 8) = pack2(dq[nt][2], dq[nt][3]);
-      }
-    }
-    __syncthreads();
-    // ---------------- phase 2: key tiles -> dK, dV ----------------
-    for (int item = warp; item < gm.G * NQ; item += nw) {
-      const int hh = item / NQ, kt = item - hh * NQ;
-      const uint32_t qb = smem_addr(sQ + hh * dh), kb = smem_addr(sK + hh * dh), vb = smem_addr(sV + hh * dh),
-                     ob = smem_addr(sdO + hh * dh);
-      const float* pm = st_m + hh * T;
-      const float* pil = st_il + hh * T;
-      const float* pdl = st_dl + hh * T;
-      uint32_t ak[KD][4], av[KD][4];
-#pragma unroll
-      for (int ks = 0; ks < KD; ++ks) {
-        ldsm_x4(ak[ks], addr_a2(kb, pb, kt * 16, T, ks * 16, lane));   // A = K rows of this key tile
-        ldsm_x4(av[ks], addr_a2(vb, pb, kt * 16, T, ks * 16, lane));   // A = V rows of this key tile
-      }
-      float dk[2 * KD][4], dv[2 * KD][4];
-#pragma unroll
-      for (int i = 0; i < 2 * KD; ++i) {
-        dk[i][0] = 0.f; dk[i][1] = 0.f; dk[i][2] = 0.f; dk[i][3] = 0.f;
-        dv[i][0] = 0.f; dv[i][1] = 0.f; dv[i][2] = 0.f; dv[i][3] = 0.f;
-      }
-      for (int qbk = 0; qbk < NQ; ++qbk) {
-        float stt[2][4] = {}, dpt[2][4] = {};          // S^T and dP^T blocks: rows = keys, cols = queries
-#pragma unroll
-        for (int ks = 0; ks < KD; ++ks) {
-          uint32_t bfr[4];
-          ldsm_x4(bfr, addr_bk2(qb, pb, qbk * 16, T, ks * 16, lane));  // B[k=c][n=query] = Q[query][c]
-          mma_bf16(stt[0], ak[ks], bfr[0], bfr[1]);
-          mma_bf16(stt[1], ak[ks], bfr[2], bfr[3]);
-          ldsm_x4(bfr, addr_bk2(ob, pb, qbk * 16, T, ks * 16, lane));  // B[k=c][n=query] = dO[query][c]
-          mma_bf16(dpt[0], av[ks], bfr[0], bfr[1]);
-          mma_bf16(dpt[1], av[ks], bfr[2], bfr[3]);
-        }
-        uint32_t pa[4], sa[4];
-#pragma unroll
-        for (int u2 = 0; u2 < 2; ++u2) {
-          float pv[4], dsv[4];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int qi = qbk * 16 + u2 * 8 + cb + e;
-            const bool ok = qi < T;
-            const float mq = ok ? pm[qi] : 0.f, il = ok ? pil[qi] : 0.f, dl = ok ? pdl[qi] : 0.f;
-            const float p0 = ok ? __expf(stt[u2][e] * scale - mq) * il : 0.f;
-            const float p1 = ok ? __expf(stt[u2][2 + e] * scale - mq) * il : 0.f;
-            pv[e] = p0; pv[2 + e] = p1;
-            dsv[e] = p0 * (dpt[u2][e] - dl) * scale;
-            dsv[2 + e] = p1 * (dpt[u2][2 + e] - dl) * scale;
-          }
-          pa[2 * u2] = pack2(pv[0], pv[1]);   pa[2 * u2 + 1] = pack2(pv[2], pv[3]);
-          sa[2 * u2] = pack2(dsv[0], dsv[1]); sa[2 * u2 + 1] = pack2(dsv[2], dsv[3]);
-        }
-#pragma unroll
-        for (int np = 0; np < KD; ++np) {
-          uint32_t bfr[4];
-          ldsm_x4_t(bfr, addr_a2(qb, pb, qbk * 16, T, np * 16, lane));   // B[k=query][n=c] = Q[query][c]
-          mma_bf16(dk[2 * np], sa, bfr[0], bfr[1]);
-          mma_bf16(dk[2 * np + 1], sa, bfr[2], bfr[3]);
-          ldsm_x4_t(bfr, addr_a2(ob, pb, qbk * 16, T, np * 16, lane));   // B[k=query][n=c] = dO[query][c]
-          mma_bf16(dv[2 * np], pa, bfr[0], bfr[1]);
-          mma_bf16(dv[2 * np + 1], pa, bfr[2], bfr[3]);
-        }
-      }
-      const int r0 = kt * 16 + g, r1 = r0 + 8;
-      bf16* okp = gK + hh * dh + cb;
-      bf16* ovp = gV + hh * dh + cb;
-#pragma unroll
-      for (int nt = 0; nt < 2 * KD; ++nt) {
-        if (r0 < T) {
-          *reinterpret_cast<uint32_t*>(okp + (size_t)r0 * pitch + nt * 8) = pack2(dk[nt][0], dk[nt][1]);
-          *reinterpret_cast<uint32_t*>(ovp + (size_t)r0 * pitch + nt * 8) = pack2(dv[nt][0], dv[nt][1]);
-        }
-        if (r1 < T) {
-          *reinterpret_cast<uint32_t*>(okp + (size_t)r1 * pitch + nt * 8) = pack2(dk[nt][2], dk[nt][3]);
-          *reinterpret_cast<uint32_t*>(ovp + (size_t)r1 * pitch + nt * 8) = pack2(dv[nt][2], dv[nt][3]);
-        }
-      }
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      bf16* dst = dqkv + (size_t)b * T * ld + hg * gm.gd;
-      for (int r = 0; r < T; ++r) {
-        bulk_s2g(dst + (size_t)r * ld, gQ + (size_t)r * pitch, rowb);
-        bulk_s2g(dst + (size_t)r * ld + d, gK + (size_t)r * pitch, rowb);
-        bulk_s2g(dst + (size_t)r * ld + 2 * d, gV + (size_t)r * pitch, rowb);
-      }
-      bulk_commit_group();
-    }
-  }
-  if (tid == 0) bulk_wait_all0();
-}
-
 // A/B switch for kernel studies (tools/probes/attn_tc5_check.py): AMC_ATTN_LEGACY=1 skips the tcgen05 kernels
 inline bool attn_legacy_only() {
   static const bool v = [] { const char* e = getenv("AMC_ATTN_LEGACY"); return e && e[0] == '1'; }();
   return v;
-}
-
-inline bool use_tc(int T, int h, int dh) {
-  return T > 16 && T <= 288 && (dh == 16 || dh == 32 || dh == 64) && (h * dh) % 8 == 0;
-}
-inline size_t tc_bytes(int T, int dh, int G, bool bwd) {
-  const size_t tile = (size_t)T * (G * dh + 8) * 2;
-  return 128 + (bwd ? 7 : 4) * tile + (bwd ? (size_t)3 * G * T * 4 : 0);
-}
-// heads per CTA: the largest divisor of h whose tiles fit ~100 KB (two CTAs per SM), at least 1
-inline int tc_group(int T, int h, int dh, bool bwd) {
-  int best = 1;
-  for (int G = 1; G <= h; ++G)
-    if (h % G == 0 && (G * dh * 2) % 16 == 0 && tc_bytes(T, dh, G, bwd) <= 100 * 1024) best = G;
-  return best;
 }
 
 // the frame kernels need 16-byte row copies: (3d, d) * sizeof(E) % 16 == 0
@@ -1325,38 +929,6 @@ int attention_fwd(int B, int T, int h, int dh, const E* qkv, E* out, float* lse,
     if (handled) return 0;
     AMC_TRY(attn_tiles_fwd(B, T, h, dh, qkv, out, lse, &handled, st));
     if (handled) return 0;
-  }
-  if constexpr (std::is_same<E, bf16>::value) {
-    // (shapes whose tiles do not fit fall through to the SIMT kernel below instead of failing)
-    if (use_tc(T, h, dh) && tc_bytes(T, dh, tc_group(T, h, dh, false), false) <= 220 * 1024) {
-      TcGeom gm;
-      gm.T = T; gm.h = h; gm.G = tc_group(T, h, dh, false); gm.gd = gm.G * dh; gm.pitch = gm.gd + 8;
-      gm.units = B * (h / gm.G);
-      const size_t sm = tc_bytes(T, dh, gm.G, false);
-      const int grid = std::min(gm.units, 148 * 2);
-      const float sc = 1.f / sqrtf((float)dh);
-      const int nb = (T + 15) / 16;
-#define AMC_TC_FWD(KD, NB)                                                                                          \
-  do {                                                                                                              \
-    AMC_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<KD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
-    attn_tc_fwd_kernel<KD, NB><<<grid, 128, sm, st>>>(gm, qkv, out, sc);                                            \
-  } while (0)
-#define AMC_TC_FWD_NB(KD)                              \
-  do {                                                 \
-    if (nb <= 2) AMC_TC_FWD(KD, 2);                    \
-    else if (nb <= 3) AMC_TC_FWD(KD, 3);               \
-    else if (nb <= 5) AMC_TC_FWD(KD, 5);               \
-    else if (nb <= 9) AMC_TC_FWD(KD, 9);               \
-    else AMC_TC_FWD(KD, 18);                           \
-  } while (0)
-      if (dh == 16) AMC_TC_FWD_NB(1);
-      else if (dh == 32) AMC_TC_FWD_NB(2);
-      else AMC_TC_FWD_NB(4);
-#undef AMC_TC_FWD_NB
-#undef AMC_TC_FWD
-      AMC_LAUNCH_CHECK();
-      return 0;
-    }
   }
   if (use_small<E>(T, h, dh)) {
     const int F = small_frames<E>(T, h, dh, small_fwd_bytes<E>);
@@ -1426,37 +998,6 @@ int attention_bwd_impl(int B, int T, int h, int dh, const E* qkv, const E* out, 
     AMC_TRY(attn_tiles_bwd(B, T, h, dh, qkv, out, lse, dout, dqkv, dbias, &handled, st));
     if (handled) {
       *fused = true;
-      return 0;
-    }
-  }
-  if constexpr (std::is_same<E, bf16>::value) {
-    if (use_tc(T, h, dh) && tc_bytes(T, dh, tc_group(T, h, dh, true), true) <= 220 * 1024) {
-      TcGeom gm;
-      gm.T = T; gm.h = h; gm.G = tc_group(T, h, dh, true); gm.gd = gm.G * dh; gm.pitch = gm.gd + 8;
-      gm.units = B * (h / gm.G);
-      const size_t sm = tc_bytes(T, dh, gm.G, true);
-      const int grid = std::min(gm.units, 148 * 2);
-      const float sc = 1.f / sqrtf((float)dh);
-      const int nb = (T + 15) / 16;
-#define AMC_TC_BWD(KD, NB)                                                                                          \
-  do {                                                                                                              \
-    AMC_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<KD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
-    attn_tc_bwd_kernel<KD, NB><<<grid, 128, sm, st>>>(gm, qkv, dout, dqkv, sc);                                     \
-  } while (0)
-#define AMC_TC_BWD_NB(KD)                              \
-  do {                                                 \
-    if (nb <= 2) AMC_TC_BWD(KD, 2);                    \
-    else if (nb <= 3) AMC_TC_BWD(KD, 3);               \
-    else if (nb <= 5) AMC_TC_BWD(KD, 5);               \
-    else if (nb <= 9) AMC_TC_BWD(KD, 9);               \
-    else AMC_TC_BWD(KD, 18);                           \
-  } while (0)
-      if (dh == 16) AMC_TC_BWD_NB(1);
-      else if (dh == 32) AMC_TC_BWD_NB(2);
-      else AMC_TC_BWD_NB(4);
-#undef AMC_TC_BWD_NB
-#undef AMC_TC_BWD
-      AMC_LAUNCH_CHECK();
       return 0;
     }
   }

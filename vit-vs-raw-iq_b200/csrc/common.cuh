@@ -96,10 +96,14 @@ struct DropoutCfg {
 inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset, bool training, const uint32_t* ctr = nullptr) {
   DropoutCfg c;
   c.ctr = ctr;
-  c.p = (training && p > 0.f) ? p : 0.f;
-  c.scale = c.p > 0.f ? 1.f / (1.f - c.p) : 1.f;
-  double t = (double)c.p * 4294967296.0;
+  // The keep test compares 16-bit fields, so the drop probability is quantised to floor(p * 65536) / 65536 (documented in
+  // include/amc_b200.h); the survivors are scaled by the QUANTISED probability, and p < 2^-16 disables dropout altogether
+  // (scaling by 1 / (1 - p) with nothing ever dropped would bias the mean).
+  double t = (training && p > 0.f) ? (double)p * 4294967296.0 : 0.0;
   c.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  const uint32_t t16 = c.thresh >> 16;
+  c.p = t16 > 0 ? (float)(t16 / 65536.0) : 0.f;
+  c.scale = t16 > 0 && t16 < 65535 ? (float)(1.0 / (1.0 - t16 / 65536.0)) : (t16 > 0 ? 65536.f : 1.f);
   c.seed_lo = (uint32_t)seed;
   c.seed_hi = (uint32_t)(seed >> 32);
   c.off_lo = (uint32_t)offset;

@@ -971,6 +971,27 @@ int ce_loss(int B, int C, const float* logits, const int64_t* labels, float ls, 
   return 0;
 }
 
+// first index of the row maximum (torch.max(1) / argmax semantics of R/training/utils.py:311-317; NaN rows give the index
+// of the first NaN, as torch does); one thread per frame -- C is 11 or 19
+__global__ void argmax_kernel(int B, int C, const float* __restrict__ logits, int64_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* r = logits + (size_t)b * C;
+  float best = r[0];
+  int bi = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = r[c];
+    if (best == best && (v > best || v != v)) { best = v; bi = c; }
+  }
+  out[b] = bi;
+}
+int argmax_rows(int B, int C, const float* logits, int64_t* out, cudaStream_t st) {
+  if (B == 0) return 0;
+  argmax_kernel<<<ceil_div(B, 128), 128, 0, st>>>(B, C, logits, out);
+  AMC_LAUNCH_CHECK();
+  return 0;
+}
+
 int cast_blob(int64_t n, const float* src, bf16* dst, cudaStream_t st) {
   AMC_CHECK_ARG(n % 4 == 0, "cast_blob: n must be a multiple of 4");
   if (n == 0) return 0;

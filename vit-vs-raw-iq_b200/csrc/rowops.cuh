@@ -41,6 +41,7 @@ int head_fwd(int B, int T, int d, int C, int has_cls, int head_ln, float eps, co
 int head_bwd(int B, int T, int d, int C, int has_cls, int head_ln, const float* dlogits, const float* W,
              const float* lnw, const float* s_hl, const float* s_xhat, const float* s_rstd, float* dhl_scratch,
              float* dxL, float* dW, float* dbias, float* dlnw, float* dlnb, cudaStream_t st);
+int argmax_rows(int B, int C, const float* logits, int64_t* out, cudaStream_t st);
 int ce_loss(int B, int C, const float* logits, const int64_t* labels, float ls, float grad_scale, float loss_scale,
             float* dlogits, float* stats, cudaStream_t st);
 int cast_blob(int64_t n, const float* src, bf16* dst, cudaStream_t st);

@@ -21,14 +21,17 @@ from .modules import _AMCBase, _DTYPES
 class TrainStep:
     def __init__(self, model: _AMCBase, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.99),
                  eps: float = 1e-8, max_norm: float = 1.0, label_smoothing: float = 0.1,
-                 process_group=None, layers_per_bucket: int = 2):
+                 process_group=None, layers_per_bucket: int = 2, data_parallel: bool = True):
+        """``data_parallel=False``: train this model on this rank alone even though ``torch.distributed`` is initialised
+        (rank-sharded hyper-parameter search: every rank holds DIFFERENT models, so no collective may be issued)."""
         self.model = model
         self.core = model._core
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.max_norm, self.ls = max_norm, label_smoothing
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if data_parallel and (process_group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         flat = model.flat_parameters()
         if not flat.is_cuda:
@@ -105,7 +108,7 @@ class TrainStep:
         flat = self.model.flat_parameters()
         st = torch.cuda.current_stream(self.dev).cuda_stream
         lib = _lib.lib
-        self.grads.zero_()
+        _lib.check(lib.amc_zero(self.grads.data_ptr(), self.grads.numel() * 4, st), "amc_zero")     # optimizer.zero_grad()
         _lib.check(lib.amc_model_fwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), core.pos_buffer().data_ptr(),
                                      ws.data_ptr(), logits.data_ptr(), 0, st), "amc_model_fwd")
         gb = B * self.world
@@ -178,7 +181,7 @@ class GraphTrainStep(TrainStep):
         flat = self.model.flat_parameters()
         st = torch.cuda.current_stream(self.dev).cuda_stream
         lib = _lib.lib
-        self.grads.zero_()
+        _lib.check(lib.amc_zero(self.grads.data_ptr(), self.grads.numel() * 4, st), "amc_zero")     # optimizer.zero_grad()
         _lib.check(lib.amc_model_fwd(C.byref(desc), src.data_ptr(), flat.data_ptr(), core.pos_buffer().data_ptr(),
                                      ws.data_ptr(), logits.data_ptr(), 0, st), "amc_model_fwd")
         _lib.check(lib.amc_ce_loss(B, core.C, logits.data_ptr(), labels.data_ptr(), self.ls, 1.0 / B, 1.0,
@@ -258,7 +261,7 @@ class HostPipeline:
         self.t.step(xs, ys)
         self.free[k].record(cur)
         self.loss_host[k].copy_(self.t.stats, non_blocking=True)
-        self.t.stats.zero_()
+        _lib.check(_lib.lib.amc_zero(self.t.stats.data_ptr(), 8, cur.cuda_stream), "amc_zero")
         self.t.frames_seen = 0
         self.loss_evt[k].record(cur)
         prev = None
@@ -361,4 +364,13 @@ def predict(model: _AMCBase, src: torch.Tensor, out: Optional[torch.Tensor] = No
     """argmax class per frame (R/training/utils.py:311-317: model.eval(); model(x).max(1))."""
     model.eval()
     logits = model(src)
-    return torch.argmax(logits, dim=1, out=out)
+    if not logits.is_cuda:
+        raise RuntimeError("predict needs the model on a CUDA device (no CPU fallback)")
+    B, ncls = logits.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    elif out.dtype != torch.int64 or out.numel() != B or not out.is_contiguous() or out.device != logits.device:
+        raise ValueError(f"out must be a contiguous int64 tensor of shape [{B}] on {logits.device}")
+    _lib.check(_lib.lib.amc_argmax(B, ncls, logits.data_ptr(), out.data_ptr(),
+                                   torch.cuda.current_stream(logits.device).cuda_stream), "amc_argmax")
+    return out

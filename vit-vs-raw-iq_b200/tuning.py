@@ -25,6 +25,7 @@ from __future__ import annotations
 import math
 import os
 import sys
+import zlib
 from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -120,9 +121,9 @@ def fast_train(model, train_ds, val_ds, lr: float, batch_size: int, device, stat
         model = model.to(device)
     model.set_raw_input(stats)
     # Adam == AdamW without decay; no clipping (max_norm 0 disables it) and no label smoothing in the sketch
+    # particles are sharded across ranks: each rank trains ITS candidates alone -- no broadcast, no gradient exchange
     trainer = TrainStep(model, lr=lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_norm=0.0,
-                        label_smoothing=0.0)
-    trainer.world = 1      # particles are sharded across ranks: each rank trains ITS candidates alone, no gradient exchange
+                        label_smoothing=0.0, data_parallel=False)
     order = torch.randperm(xt.shape[0], generator=torch.Generator().manual_seed(seed))
     for i in range(max_batches):
         idx = order[i * batch_size:(i + 1) * batch_size]
@@ -148,6 +149,9 @@ def fitness_function(X: np.ndarray, train_ds, val_ds, rawiq_cfg: Dict, vit_cfg: 
             hp = repair_params(p, rawiq_cfg, vit_cfg)
             if os.environ.get("AMC_TUNING_VERBOSE"):
                 print(f"[tuning rank {os.environ.get('RANK', '0')}] {hp}", file=sys.stderr, flush=True)
+            # initial weights and dropout masks are a function of the candidate alone, so a score does not depend on
+            # which rank evaluates it or on what that rank evaluated before
+            torch.manual_seed(zlib.crc32(np.ascontiguousarray(p, dtype=np.float64).tobytes()))
             model = build_models(p, rawiq_cfg, vit_cfg)
             return fast_train(model, train_ds, val_ds, hp["lr"], hp["batch_size"], device)
     dist = torch.distributed
@@ -227,12 +231,19 @@ def main(argv=None) -> None:
     ap.add_argument("--val-frames", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args(argv)
+    # AMC_TUNING_BACKEND=gloo: score exchange over gloo, ranks wrap around the visible GPUs (several ranks may share one)
+    backend = os.environ.get("AMC_TUNING_BACKEND", "nccl")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend != "nccl":
+        local_rank %= max(1, torch.cuda.device_count())
     dist = torch.distributed
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
     device = f"cuda:{local_rank}"
     X, y, _ = synth.make_frames(a.train_frames + a.val_frames, classes=synth.CLASSES_11, seed=42)   # same data on every rank
     train, val = (X[:a.train_frames], y[:a.train_frames]), (X[a.train_frames:], y[a.train_frames:])
