@@ -14,12 +14,17 @@ OUT=gpurun_out
 mkdir -p "$OUT"
 WORKLOADS="rawiq_seg16_d128_L6 vit_p4_d128_L6 rawiq_sps1_seg8_d256_L6 rawiq_sps2_seg8_d256_L6 rawiq_seg16_d512_L12 rawiq_conv1d_d128_L6"
 
+# ncu reports with sources are tens of MB each and gpurun copies back at most 64 MiB: keep the raw-metric CSV, drop the report
+rep2csv() { [ -s "$1.ncu-rep" ] && ncu -i "$1.ncu-rep" --page raw --csv > "$1.csv" 2>/dev/null; rm -f "$1.ncu-rep"; }
+
 if [ "$MODE" = collect ]; then
   timeout 400 python -m pytest tests -m gpu -q -x > "$OUT/${TAG}_pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/${TAG}_status.txt"
   timeout 120 python __graft_entry__.py smoke > "$OUT/${TAG}_smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/${TAG}_status.txt"
   timeout 300 python bench.py > "$OUT/${TAG}_bench_1gpu.json" 2> "$OUT/${TAG}_bench_1gpu.err"; echo "bench rc=$?" | tee -a "$OUT/${TAG}_status.txt"
   timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/${TAG}_bench_reference_arm.json" 2>> "$OUT/${TAG}_bench_1gpu.err"
   echo "reference arm rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 200 python bench.py --dtype fp32 --no-cpu-baseline --steps 10 --warmup 3 > "$OUT/${TAG}_bench_1gpu_fp32.json" 2>> "$OUT/${TAG}_bench_1gpu.err"
+  echo "fp32 bench rc=$?" | tee -a "$OUT/${TAG}_status.txt"
   for W in $WORKLOADS; do
     timeout 120 python bench.py --workload "$W" --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_wl_${W}.json" 2>> "$OUT/${TAG}_wl.err"
     echo "workload $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
@@ -32,10 +37,13 @@ if [ "$MODE" = collect ]; then
     timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off -f -k regex:gemm_tc_kernel -c 8 \
       -o "$OUT/${TAG}_full_wgrad" python tools/one_step.py > "$OUT/${TAG}_ncu_full_wgrad.log" 2>&1
     echo "ncu full wgrad rc=$?" | tee -a "$OUT/${TAG}_status.txt"
-    # full capture of the default step: the GEMM / LayerNorm / front-end classes at the bench batch (attention is T = 9 here)
-    timeout 420 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
-      -o "$OUT/${TAG}_full_step" python tools/one_step.py ${NCU_BATCH:+--batch $NCU_BATCH} > "$OUT/${TAG}_ncu_full.log" 2>&1
+    rep2csv "$OUT/${TAG}_full_wgrad"
+    # the other classes of the default step (GEMM epilogues, LayerNorm, front end, T = 9 attention): first 70 launches of a
+    # step at 8192 frames (the whole step at the bench batch does not finish in 7 minutes under --set full)
+    timeout 300 ncu --set full --clock-control none --profile-from-start off -f -c 70 \
+      -o "$OUT/${TAG}_full_step" python tools/one_step.py --batch 8192 > "$OUT/${TAG}_ncu_full.log" 2>&1
     echo "ncu full rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+    rep2csv "$OUT/${TAG}_full_step"
   else
     echo "one_step.py failed without ncu: no ncu passes" | tee -a "$OUT/${TAG}_status.txt"
   fi
@@ -49,6 +57,7 @@ if [ "$MODE" = collect ]; then
       timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -f -k regex:attn_ \
         -o "$OUT/${TAG}_full_attn_${W}" python tools/one_step.py --workload $W > "$OUT/${TAG}_ncu_full_${W}.log" 2>&1
       echo "ncu full attention $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+      rep2csv "$OUT/${TAG}_full_attn_${W}"
     fi
   done
   nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/${TAG}_nvidia_smi.csv" 2>&1
@@ -104,15 +113,17 @@ elif [ "$MODE" = summarise ]; then
   [ -s "$OUT/${TAG}_launches_train.csv" ] && cp "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.csv" && \
     python tools/ncu_summary.py launches "$OUT/${TAG}_launches_train.csv" "profiles/${TAG}_launches_train.md" \
       --title "${TAG}: ncu launch list of one training step (tools/one_step.py, default workload)"
-  [ -s "$OUT/${TAG}_full_wgrad.ncu-rep" ] && \
-    python tools/ncu_summary.py full "$OUT/${TAG}_full_wgrad.ncu-rep" "profiles/${TAG}_ncu_full_wgrad.json"
-  [ -s "$OUT/${TAG}_full_step.ncu-rep" ] && \
-    python tools/ncu_summary.py full "$OUT/${TAG}_full_step.ncu-rep" "profiles/${TAG}_ncu_full_step.json"
+  cp "$OUT/${TAG}_bench_1gpu_fp32.json" "profiles/${TAG}_bench_1gpu_fp32.json"
+  [ -s "$OUT/${TAG}_full_step.csv" ] && \
+    python tools/ncu_summary.py full "$OUT/${TAG}_full_step.csv" "profiles/${TAG}_ncu_full_step.json" --batch 8192
+  # (after the whole-step summary: the bench-batch capture of the dominant class is the one bench.py reads)
+  [ -s "$OUT/${TAG}_full_wgrad.csv" ] && \
+    python tools/ncu_summary.py full "$OUT/${TAG}_full_wgrad.csv" "profiles/${TAG}_ncu_full_wgrad.json"
   for W in rawiq_sps1_seg8_d256_L6 rawiq_sps2_seg8_d256_L6; do
     [ -s "$OUT/${TAG}_launches_${W}.csv" ] && python tools/ncu_summary.py launches "$OUT/${TAG}_launches_${W}.csv" \
       "profiles/${TAG}_launches_train_${W}.md" --title "${TAG}: ncu launch list of one training step (tools/one_step.py --workload $W)"
-    [ -s "$OUT/${TAG}_full_attn_${W}.ncu-rep" ] && \
-      python tools/ncu_summary.py full "$OUT/${TAG}_full_attn_${W}.ncu-rep" "profiles/${TAG}_ncu_full_attn_${W}.json" --workload $W
+    [ -s "$OUT/${TAG}_full_attn_${W}.csv" ] && \
+      python tools/ncu_summary.py full "$OUT/${TAG}_full_attn_${W}.csv" "profiles/${TAG}_ncu_full_attn_${W}.json" --workload $W
   done
   tail -3 "$OUT/${TAG}_pytest_gpu.log"
 else

@@ -87,7 +87,9 @@ ALT = {"sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_act
 
 
 def full(rep, out, workload, frames=0):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a report, or the `ncu -i report --page raw --csv` text made from it on the GPU box (reports are too big to bring back)
+    txt = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")

@@ -1180,17 +1180,22 @@ void tc5_trace_end(long long* buf, const char* what, int T, int dh, cudaStream_t
 
 }  // namespace
 
-// Where the tcgen05 kernels are the faster ones (B200, tools/probes/attn_tc5_check.py --bwd --time): everything from
-// T = 81 up; for T <= 80 only head dim 64 (one 128-lane tile per unit is half empty there and the mma.sync tile kernels
-// win at head dim 16 / 32).  AMC_ATTN_TC5=all|none overrides for kernel studies.
-bool tc5_preferred(int T, int dh) {
+// Where the tcgen05 kernels are the faster ones (B200, tools/probes/attn_tc5_check.py --bwd --time; profiles/
+// r2_attn_tc5_check_and_timing.txt), per direction -- both forward kernels write the same log2-domain lse, so a tcgen05
+// forward pairs with either backward:
+//   forward : T > 80, and head dim 64 at any T (T = 65, dh = 64: 141 vs 196 us)
+//   backward: head dim 32 at T > 80 (T = 129: 298 vs 373 us, T = 257: 393 vs 598 us); at head dim 16 the item's fixed
+//             barrier / MMA cost is spread over half the bytes (T = 129: 263 vs 212 us) and at dh = 64, T <= 80 the
+//             half-empty 128-lane tile loses (897 vs 551 us): the mma.sync tile kernels keep those.
+// AMC_ATTN_TC5=all|none overrides for kernel studies.
+bool tc5_preferred(int T, int dh, bool bwd) {
   static const int mode = [] {
     const char* e = getenv("AMC_ATTN_TC5");
     return e == nullptr ? 0 : (e[0] == 'a' ? 1 : (e[0] == 'n' ? 2 : 0));
   }();
   if (mode == 1) return true;
   if (mode == 2) return false;
-  return T > 80 || dh == 64;
+  return bwd ? (T > 80 && dh == 32) : (T > 80 || dh == 64);
 }
 
 bool attn_tc5_supported(int T, int h, int dh) {
@@ -1203,7 +1208,7 @@ int attn_tc5_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float*
   *handled = false;
   Tc5Geom g;
   int RM = 0;
-  if (!tc5_plan(B, T, h, dh, g, RM) || !tc5_preferred(T, dh)) return 0;
+  if (!tc5_plan(B, T, h, dh, g, RM) || !tc5_preferred(T, dh, false)) return 0;
   const size_t sm = tc5_fwd_bytes(g);
   if (sm > TC5_SMEM_MAX || (g.d * 2) % 16 != 0) return 0;
   CUtensorMap mQ, mQlo, mKV, mO;
@@ -1249,7 +1254,7 @@ int attn_tc5_bwd(int B, int T, int h, int dh, const bf16* qkv, const bf16* out, 
                  bf16* dqkv, float* dbias, bool* handled, cudaStream_t st) {
   *handled = false;
   Tc5BwdGeom g;
-  if (out == nullptr || lse == nullptr || !tc5_bwd_plan(B, T, h, dh, g) || !tc5_preferred(T, dh)) return 0;
+  if (out == nullptr || lse == nullptr || !tc5_bwd_plan(B, T, h, dh, g) || !tc5_preferred(T, dh, true)) return 0;
   const size_t sm = tc5_bwd_bytes(g);
   if (sm > TC5_SMEM_MAX || (g.d * 2) % 16 != 0) return 0;
   CUtensorMap mQKV, mDO, mOut;
