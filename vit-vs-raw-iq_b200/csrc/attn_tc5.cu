@@ -1184,9 +1184,11 @@ void tc5_trace_end(long long* buf, const char* what, int T, int dh, cudaStream_t
 // r2_attn_tc5_check_and_timing.txt), per direction -- both forward kernels write the same log2-domain lse, so a tcgen05
 // forward pairs with either backward:
 //   forward : T > 80, and head dim 64 at any T (T = 65, dh = 64: 141 vs 196 us)
-//   backward: head dim 32 at T > 80 (T = 129: 298 vs 373 us, T = 257: 393 vs 598 us); at head dim 16 the item's fixed
-//             barrier / MMA cost is spread over half the bytes (T = 129: 263 vs 212 us) and at dh = 64, T <= 80 the
-//             half-empty 128-lane tile loses (897 vs 551 us): the mma.sync tile kernels keep those.
+//   backward: head dim 32 at T > 80 (T = 129: 298 vs 373 us, T = 257: 393 vs 598 us) and head dim 64 (inside a training
+//             step of the d512 / h8 grid corner, T = 65: 295 vs 311 us per layer -- the isolated probe, cold inputs, says the
+//             opposite, 897 vs 551 us at twice the batch; the step is what counts); at head dim 16 the item's fixed
+//             barrier / MMA cost is spread over half the bytes (T = 129: 263 vs 212 us isolated, 257 vs 214 us inside the
+//             production-ViT step): the mma.sync tile kernels keep that.
 // AMC_ATTN_TC5=all|none overrides for kernel studies.
 bool tc5_preferred(int T, int dh, bool bwd) {
   static const int mode = [] {
@@ -1195,7 +1197,7 @@ bool tc5_preferred(int T, int dh, bool bwd) {
   }();
   if (mode == 1) return true;
   if (mode == 2) return false;
-  return bwd ? (T > 80 && dh == 32) : (T > 80 || dh == 64);
+  return bwd ? (dh == 64 || (T > 80 && dh == 32)) : (T > 80 || dh == 64);
 }
 
 bool attn_tc5_supported(int T, int h, int dh) {

@@ -312,20 +312,24 @@ struct RowParams {
   int n_cols;          // N (size of the shared-memory column accumulator)
 };
 
-template <int BN, int RE> struct RowCfg {
+template <int BN, int RE, int W = 8> struct RowCfg {
   static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   // bf16-output epilogues are instruction-heavy (dropout hash, mask tests, packing): two warps per TMEM
   // lane quadrant alternate over the 32-column chunks; the fp32 / LayerNorm epilogues keep one warp per
   // quadrant (the row statistics stay thread-local).
-  static constexpr int NEPI = (RE == RE_BF16 || RE == RE_MASK) ? 8 : 4;
-  static constexpr int EPW = (NEPI == 8) ? 8192 : 16384;   // epilogue bytes per warp
-  static constexpr int IN_STRIDE = (NEPI == 8) ? 2048 : 4096;
-  static constexpr int OUT_OFF = (NEPI == 8) ? 4096 : 8192;
+  // The bf16 epilogue with ReLU / dropout (FFN1) runs W = 16 warps, four per quadrant: it needs no input slab (4 KB of
+  // staging per warp), and with 2 warps per scheduler its TMEM-load -> bias / ReLU / dropout hash -> stage -> TMA-store chain
+  // left the issue slots two thirds idle (FFN1 0.283 -> 0.248 ms at the bench size).  Without the elementwise work (QKV,
+  // dgrad out-proj) 16 warps only add barrier / store-issue overhead (+5 %), so those keep W = 8.
+  static constexpr int NEPI = (RE == RE_BF16) ? W : (RE == RE_MASK ? 8 : 4);
+  static constexpr int EPW = (NEPI == 16) ? 4096 : ((NEPI == 8) ? 8192 : 16384);   // epilogue bytes per warp
+  static constexpr int IN_STRIDE = (NEPI >= 8) ? 2048 : 4096;
+  static constexpr int OUT_OFF = (NEPI == 16) ? 0 : ((NEPI == 8) ? 4096 : 8192);
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + NEPI * EPW;
-  static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), 8-warp variants
-  static constexpr int CS_BYTES = (NEPI == 8) ? 8192 : 0;
+  static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), bf16-output variants
+  static constexpr int CS_BYTES = (NEPI >= 8) ? 8192 : 0;
   static constexpr int SMEM_BYTES = CS_OFF + CS_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int THREADS = 64 + 32 * NEPI;
@@ -366,13 +370,13 @@ __device__ __forceinline__ uint32_t slab16_addr(uint32_t base, int row, int chun
   return base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-template <int BN, int RE>
-__global__ void __launch_bounds__((RowCfg<BN, RE>::THREADS), 1)
+template <int BN, int RE, int W = 8>
+__global__ void __launch_bounds__((RowCfg<BN, RE, W>::THREADS), 1)
 gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapO16,
                    const __grid_constant__ CUtensorMap mapO32, const __grid_constant__ CUtensorMap mapXh,
                    const TcParams p, const RowParams rp) {
-  using C = RowCfg<BN, RE>;
+  using C = RowCfg<BN, RE, W>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                          ~(uintptr_t)1023);
@@ -740,9 +744,9 @@ int launch(const GemmArgs& g, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int RE>
+template <int BN, int RE, int W = 8>
 int launch_row(const GemmArgs& g, cudaStream_t st) {
-  using C = RowCfg<BN, RE>;
+  using C = RowCfg<BN, RE, W>;
   const Epi& e = g.epi;
   CUtensorMap mapA, mapB, mapIn, mapO16, mapO32, mapXh;
   AMC_TRY(make_map(&mapA, g.A, g.M, g.K, g.lda, BK, BM));
@@ -772,18 +776,18 @@ int launch_row(const GemmArgs& g, cudaStream_t st) {
   const long long tiles = (long long)p.tiles_m * p.tiles_n;
   AMC_CHECK_ARG(tiles < (1ll << 30), "gemm_bf16: too many tiles");
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  auto kern = gemm_tc_row_kernel<BN, RE>;
+  auto kern = gemm_tc_row_kernel<BN, RE, W>;
   AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mapA, mapB, mapIn, mapO16, mapO32, mapXh, p, rp);
   AMC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int RE>
+template <int RE, int W = 8>
 int launch_row_bn(int bn, const GemmArgs& g, cudaStream_t st) {
-  if (bn == 256) return launch_row<256, RE>(g, st);
-  if (bn == 128) return launch_row<128, RE>(g, st);
-  return launch_row<64, RE>(g, st);
+  if (bn == 256) return launch_row<256, RE, W>(g, st);
+  if (bn == 128) return launch_row<128, RE, W>(g, st);
+  return launch_row<64, RE, W>(g, st);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -820,7 +824,8 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
     if (e.mask_src && !e.res32 && e.D16 && !e.D32 && !e.bias && !e.relu && e.drop.p == 0.f)
       return launch_row_bn<RE_MASK>(best, g, st);
     if (e.res32 && !e.mask_src && e.D32 && !e.D16 && !e.relu) return launch_row_bn<RE_RES32>(best, g, st);
-    if (!e.res32 && !e.mask_src && e.D16 && !e.D32) return launch_row_bn<RE_BF16>(best, g, st);
+    if (!e.res32 && !e.mask_src && e.D16 && !e.D32)
+      return (e.relu || e.drop.p > 0.f) ? launch_row_bn<RE_BF16, 16>(best, g, st) : launch_row_bn<RE_BF16, 8>(best, g, st);
   }
   const int mn = g.transA ? 1 : 0;
   AMC_CHECK_ARG(e.colsum_out == nullptr || mn, "gemm_bf16: fused column sums are not available for this epilogue");
