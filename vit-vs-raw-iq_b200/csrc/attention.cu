@@ -857,8 +857,13 @@ inline size_t mma_bwd_bytes(int T, int h, int dh, int F) {
   return 128 + ((size_t)2 * F * T * (3 * d + 8) + (size_t)F * T * (d + 8)) * 2 + 8 * 2 * 16 * 24 * 2;
 }
 inline int mma_frames(int T, int h, int dh, bool bwd) {
-  int F = std::max(1, ceil_div(16, h));                 // at least ~2 pairs per warp
-  while (F < 8 && (bwd ? mma_bwd_bytes(T, h, dh, F + 1) : mma_fwd_bytes(T, h, dh, F + 1)) <= 100 * 1024) ++F;
+  // AMC_MMA_SMEM_KB (kernel study): shared-memory target per CTA = how many CTAs share an SM
+  static const int lim_fwd = [] { const char* e = getenv("AMC_MMA_SMEM_KB"); return (e ? atoi(e) : 100) * 1024; }();
+  static const int lim_bwd = [] { const char* e = getenv("AMC_MMA_SMEM_KB_BWD"); const char* f = getenv("AMC_MMA_SMEM_KB");
+                                  return (e ? atoi(e) : (f ? atoi(f) : 100)) * 1024; }();
+  static const int fmin = [] { const char* e = getenv("AMC_MMA_FMIN"); return e ? atoi(e) : 0; }();
+  int F = fmin > 0 ? fmin : std::max(1, ceil_div(16, h));                 // at least ~2 pairs per warp
+  while (F < 8 && (bwd ? mma_bwd_bytes(T, h, dh, F + 1) : mma_fwd_bytes(T, h, dh, F + 1)) <= (size_t)(bwd ? lim_bwd : lim_fwd)) ++F;
   return F;
 }
 // resident CTAs per SM for a given dynamic shared-memory size (256 threads each)
