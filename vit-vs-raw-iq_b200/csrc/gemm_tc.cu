@@ -322,10 +322,15 @@ template <int BN, int RE, int W = 8> struct RowCfg {
   // staging per warp), and with 2 warps per scheduler its TMEM-load -> bias / ReLU / dropout hash -> stage -> TMA-store chain
   // left the issue slots two thirds idle (FFN1 0.283 -> 0.248 ms at the bench size).  Without the elementwise work (QKV,
   // dgrad out-proj) 16 warps only add barrier / store-issue overhead (+5 %), so those keep W = 8.
-  static constexpr int NEPI = (RE == RE_BF16) ? W : (RE == RE_MASK ? 8 : 4);
+  // The ReLU-mask epilogue (dgrad FFN2: mask test + bias-gradient column sums per element) takes 16 warps too, with its
+  // 2 KB mask slab and its output staging SINGLE-buffered (16 x 4 KB next to three operand stages): the next slab is
+  // requested as soon as the current one is in registers, four warps per scheduler cover its latency.
+  static constexpr int NEPI = (RE == RE_BF16 || RE == RE_MASK) ? W : 4;
   static constexpr int EPW = (NEPI == 16) ? 4096 : ((NEPI == 8) ? 8192 : 16384);   // epilogue bytes per warp
   static constexpr int IN_STRIDE = (NEPI >= 8) ? 2048 : 4096;
-  static constexpr int OUT_OFF = (NEPI == 16) ? 0 : ((NEPI == 8) ? 4096 : 8192);
+  static constexpr int IN_BUFS = (NEPI == 16) ? 1 : 2;
+  static constexpr int OUT_BUFS = (NEPI == 16 && RE == RE_MASK) ? 1 : 2;
+  static constexpr int OUT_OFF = (NEPI == 16) ? (RE == RE_MASK ? 2048 : 0) : ((NEPI == 8) ? 4096 : 8192);
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + NEPI * EPW;
   static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), bf16-output variants
@@ -444,7 +449,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     auto issue_in = [&](int t, int c, uint32_t gi) {
       uint64_t* nb = my_in_bar + (gi & 1);
       mbar_expect_tx(nb, IN_BYTES);
-      tma_load_2d(&mapIn, nb, egen + (gi & 1) * C::IN_STRIDE, (t % p.tiles_n) * BN + c * 32,
+      tma_load_2d(&mapIn, nb, egen + (C::IN_BUFS == 2 ? (gi & 1) : 0) * C::IN_STRIDE, (t % p.tiles_n) * BN + c * 32,
                   (t / p.tiles_n) * BM + quad * 32);
     };
     if (HAS_IN && lane == 0) {                        // first input slab
@@ -474,11 +479,19 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         if (HAS_IN) {
           // prefetch this warp's next input slab (same tile, or the first chunk of its next tile)
-          if (lane == 0) {
+          if (C::IN_BUFS == 2 && lane == 0) {
             int t = tile, c = ci + NSPLIT;
             if (next_chunk(t, c)) issue_in(t, c, g + 1);
           }
           mbar_wait(my_in_bar + (g & 1), (g >> 1) & 1);
+        }
+        uint32_t mw[16];                                // RE_MASK: this thread's 32 mask values (bf16 pairs)
+        if (RE == RE_MASK) {
+          const uint32_t ib = ebase + (C::IN_BUFS == 2 ? (g & 1) : 0) * C::IN_STRIDE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(mw[4 * k]), "=r"(mw[4 * k + 1]), "=r"(mw[4 * k + 2]),
+                         "=r"(mw[4 * k + 3]) : "r"(slab16_addr(ib, lane, k)));
         }
         tmem_ld_wait();
         float v[32];
@@ -503,13 +516,9 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         }
         if (RE == RE_MASK) {
-          const uint32_t ib = ebase + (g & 1) * C::IN_STRIDE;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                         : "r"(slab16_addr(ib, lane, k)));
-            const uint32_t w[4] = {w0, w1, w2, w3};
+            const uint32_t w[4] = {mw[4 * k], mw[4 * k + 1], mw[4 * k + 2], mw[4 * k + 3]};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               // bf16 > 0  <=>  sign bit clear and magnitude non-zero
@@ -518,6 +527,15 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               const bool phi = (hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0;
               v[8 * k + 2 * t] = plo ? v[8 * k + 2 * t] * rp.mask_scale : 0.f;
               v[8 * k + 2 * t + 1] = phi ? v[8 * k + 2 * t + 1] * rp.mask_scale : 0.f;
+            }
+          }
+          if (C::IN_BUFS == 1) {
+            // single slab buffer: every lane has consumed its mask words (the selects above depend on them), so the
+            // buffer can take this warp's next slab; the column sums, packing and the store below cover its latency
+            __syncwarp();
+            if (lane == 0) {
+              int t = tile, c = ci + NSPLIT;
+              if (next_chunk(t, c)) issue_in(t, c, g + 1);
             }
           }
         }
@@ -571,8 +589,11 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             bulk_commit();
           }
         } else {
-          const uint32_t ob = ebase + C::OUT_OFF + (g & 1) * 2048;
-          if (lane == 0) bulk_wait_read<1>();
+          const uint32_t ob = ebase + C::OUT_OFF + (C::OUT_BUFS == 2 ? (g & 1) : 0) * 2048;
+          if (lane == 0) {
+            if (C::OUT_BUFS == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -822,7 +843,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
   }
   if (row_ok) {
     if (e.mask_src && !e.res32 && e.D16 && !e.D32 && !e.bias && !e.relu && e.drop.p == 0.f)
-      return launch_row_bn<RE_MASK>(best, g, st);
+      return launch_row_bn<RE_MASK, 16>(best, g, st);
     if (e.res32 && !e.mask_src && e.D32 && !e.D16 && !e.relu) return launch_row_bn<RE_RES32>(best, g, st);
     if (!e.res32 && !e.mask_src && e.D16 && !e.D32)
       return (e.relu || e.drop.p > 0.f) ? launch_row_bn<RE_BF16, 16>(best, g, st) : launch_row_bn<RE_BF16, 8>(best, g, st);
