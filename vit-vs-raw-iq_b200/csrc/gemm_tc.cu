@@ -313,7 +313,9 @@ struct RowParams {
 };
 
 template <int BN, int RE, int W = 8> struct RowCfg {
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  // (the two-warps-per-quadrant LayerNorm epilogue pays for its second set of slabs with one operand stage)
+  static constexpr bool LN8 = (RE == RE_LN && W == 8);
+  static constexpr int STAGES = LN8 ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   // bf16-output epilogues are instruction-heavy (dropout hash, mask tests, packing): two warps per TMEM
   // lane quadrant alternate over the 32-column chunks; the fp32 / LayerNorm epilogues keep one warp per
@@ -325,16 +327,20 @@ template <int BN, int RE, int W = 8> struct RowCfg {
   // The ReLU-mask epilogue (dgrad FFN2: mask test + bias-gradient column sums per element) takes 16 warps too, with its
   // 2 KB mask slab and its output staging SINGLE-buffered (16 x 4 KB next to three operand stages): the next slab is
   // requested as soon as the current one is in registers, four warps per scheduler cover its latency.
-  static constexpr int NEPI = (RE == RE_BF16 || RE == RE_MASK) ? W : 4;
-  static constexpr int EPW = (NEPI == 16) ? 4096 : ((NEPI == 8) ? 8192 : 16384);   // epilogue bytes per warp
-  static constexpr int IN_STRIDE = (NEPI >= 8) ? 2048 : 4096;
-  static constexpr int IN_BUFS = (NEPI == 16) ? 1 : 2;
+  // The LayerNorm epilogue (three passes over the row) takes W = 8 = two warps per quadrant for K <= 256 (out-proj): each
+  // warp owns every other 32-column chunk of its rows through all three passes and the two partial row sums / sums of
+  // squares are exchanged through the partner's (idle until pass C) staging area around a 64-thread named barrier.
+  static constexpr bool WIDE = (RE == RE_RES32 || RE == RE_LN);        // fp32 slabs: 4 KB in, 4 + 2 + 2 KB out
+  static constexpr int NEPI = WIDE ? (LN8 ? 8 : 4) : W;
+  static constexpr int EPW = WIDE ? 16384 : ((NEPI == 16) ? 4096 : 8192);   // epilogue bytes per warp
+  static constexpr int IN_STRIDE = WIDE ? 4096 : 2048;
+  static constexpr int IN_BUFS = (!WIDE && NEPI == 16) ? 1 : 2;
   static constexpr int OUT_BUFS = (NEPI == 16 && RE == RE_MASK) ? 1 : 2;
-  static constexpr int OUT_OFF = (NEPI == 16) ? (RE == RE_MASK ? 2048 : 0) : ((NEPI == 8) ? 4096 : 8192);
+  static constexpr int OUT_OFF = WIDE ? 8192 : ((NEPI == 16) ? (RE == RE_MASK ? 2048 : 0) : 4096);
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + NEPI * EPW;
   static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), bf16-output variants
-  static constexpr int CS_BYTES = (NEPI >= 8) ? 8192 : 0;
+  static constexpr int CS_BYTES = WIDE ? 0 : 8192;
   static constexpr int SMEM_BYTES = CS_OFF + CS_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int THREADS = 64 + 32 * NEPI;
@@ -611,11 +617,24 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (RE == RE_LN) {
         // ---------------- pass B: variance around the exact mean (layers_norm.py:12-13) --------------
         tmem_st_wait();
+        // two warps per quadrant: each has summed its own chunks; swap the partial sums through the staging areas (the
+        // xhat staging of each warp: idle until pass C, its last TMA store has long read it -- confirmed, not assumed)
+        const uint32_t xch_mine = ebase + 14336, xch_peer = smem_u32(smem + C::EPI_OFF + (ew ^ 4) * C::EPW) + 14336;
+        auto swap_partial = [&](float mine, int slot) -> float {
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine + (uint32_t)((slot * 32 + lane) * 4)), "f"(mine) : "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          float other;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_peer + (uint32_t)((slot * 32 + lane) * 4)) : "memory");
+          return mine + other;
+        };
+        if (NSPLIT == 2) sum = swap_partial(sum, 0);
         const float inv_n = 1.f / (float)p.N;
         const float mean = sum * inv_n;
         float sq = 0.f;
 #pragma unroll 1
-        for (int ci = 0; ci < nchunks; ++ci) {
+        for (int ci = half; ci < nchunks; ci += NSPLIT) {
           uint32_t r[32];
           tmem_ld32(taddr + ci * 32, r);
           tmem_ld_wait();
@@ -625,12 +644,14 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             sq = fmaf(t, t, sq);
           }
         }
+        if (NSPLIT == 2) sq = swap_partial(sq, 1);
         const float rstd = rsqrtf(sq * inv_n + rp.ln_eps);
-        if (rp.rstd && m < p.M) rp.rstd[m] = rstd;
+        if (rp.rstd && m < p.M && half == 0) rp.rstd[m] = rstd;
         // ---------------- pass C: normalise, scale/shift, write y32 / y16 / xhat ---------------------
         const uint32_t o32 = ebase + 8192, o16 = ebase + 12288, oxh = ebase + 14336;
+        if (NSPLIT == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the peer has read slot 1: staging may be reused
 #pragma unroll 1
-        for (int ci = 0; ci < nchunks; ++ci) {
+        for (int ci = half; ci < nchunks; ci += NSPLIT) {
           const int n = n0 + ci * 32;
           uint32_t r[32];
           tmem_ld32(taddr + ci * 32, r);
@@ -839,12 +860,14 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
     AMC_CHECK_ARG(row_ok && e.res32 && e.D16 && e.D32 && !e.mask_src && !e.relu && g.N <= 256 && al16(e.ln_gamma) &&
                       al16(e.ln_beta) && (!e.ln_xhat || al16(e.ln_xhat)),
                   "gemm_bf16: fused LayerNorm epilogue needs N %% 32 == 0, N <= 256, residual, D16 and D32");
-    return launch_row_bn<RE_LN>(g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256), g, st);
+    const int bn_ln = g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256);
+    // two epilogue warps per quadrant where the main loop is short (out-proj: K = d); FFN2 (K = F) keeps its third stage
+    return g.K <= 256 ? launch_row_bn<RE_LN, 8>(bn_ln, g, st) : launch_row_bn<RE_LN, 4>(bn_ln, g, st);
   }
   if (row_ok) {
     if (e.mask_src && !e.res32 && e.D16 && !e.D32 && !e.bias && !e.relu && e.drop.p == 0.f)
       return launch_row_bn<RE_MASK, 16>(best, g, st);
-    if (e.res32 && !e.mask_src && e.D32 && !e.D16 && !e.relu) return launch_row_bn<RE_RES32>(best, g, st);
+    if (e.res32 && !e.mask_src && e.D32 && !e.D16 && !e.relu) return launch_row_bn<RE_RES32, 4>(best, g, st);
     if (!e.res32 && !e.mask_src && e.D16 && !e.D32)
       return (e.relu || e.drop.p > 0.f) ? launch_row_bn<RE_BF16, 16>(best, g, st) : launch_row_bn<RE_BF16, 8>(best, g, st);
   }
