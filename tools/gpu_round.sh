@@ -62,6 +62,30 @@ if [ "$MODE" = collect ]; then
   done
   nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/${TAG}_nvidia_smi.csv" 2>&1
   cat "$OUT/${TAG}_status.txt"
+elif [ "$MODE" = refresh ]; then
+  # after a kernel change late in a round: tests, smoke, the bench lines, the default launch list and a full capture of the
+  # row-epilogue GEMMs only (the other captures of `collect` stay valid)
+  timeout 400 python -m pytest tests -m gpu -q -x > "$OUT/${TAG}_pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 120 python __graft_entry__.py smoke > "$OUT/${TAG}_smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 300 python bench.py > "$OUT/${TAG}_bench_1gpu.json" 2> "$OUT/${TAG}_bench_1gpu.err"; echo "bench rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  for W in $WORKLOADS; do
+    timeout 120 python bench.py --workload "$W" --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_wl_${W}.json" 2>> "$OUT/${TAG}_wl.err"
+    echo "workload $W rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  done
+  for B in 256 2048; do
+    timeout 120 python bench.py --workload rawiq_seg16_d128_L6 --batch $B --graph --steps 20 --warmup 5 --no-cpu-baseline \
+      > "$OUT/${TAG}_wl_rawiq_seg16_d128_L6_B${B}_graph.json" 2>> "$OUT/${TAG}_wl.err"
+    echo "graph step B=$B rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  done
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file "$OUT/${TAG}_launches_train.csv" python tools/one_step.py > "$OUT/${TAG}_ncu_launch.log" 2>&1
+  echo "ncu launch list rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  timeout 240 ncu --set full --clock-control none --profile-from-start off -f -k regex:gemm_tc_row_kernel -c 42 \
+    -o "$OUT/${TAG}_full_rowgemm" python tools/one_step.py --batch 8192 > "$OUT/${TAG}_ncu_full_rowgemm.log" 2>&1
+  echo "ncu full row GEMMs rc=$?" | tee -a "$OUT/${TAG}_status.txt"
+  rep2csv "$OUT/${TAG}_full_rowgemm"
+  nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/${TAG}_nvidia_smi.csv" 2>&1
+  cat "$OUT/${TAG}_status.txt"
 elif [ "$MODE" = sanitize ]; then
   # memcheck + racecheck over the op-level tests at their smallest shapes (the sanitizer slows kernels
   # 10-100x: a bounded subset, each tool under its own timeout).  gpurun --timeout 900 -- 'bash tools/gpu_round.sh sanitize r2'

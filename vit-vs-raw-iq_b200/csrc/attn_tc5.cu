@@ -47,7 +47,7 @@ struct Tc5Geom {
   float sl2;                      // log2(e) / sqrt(dh)
 };
 
-constexpr int TC5_HDR = 1024;     // mbarriers + TMEM slot
+constexpr int TC5_HDR = 4096;     // mbarriers + TMEM slot (256 B), then the split-row exchange: [max | sum][half][128 rows] floats
 
 // ---- PTX not in tc_ptx.cuh ------------------------------------------------------------------------------------
 // shared-memory matrix descriptor with an explicit swizzle mode (2 = 128B, 4 = 64B, 6 = 32B)
@@ -151,17 +151,21 @@ __device__ __forceinline__ void tr(long long* trace, int role, int it, int ev) {
   if (trace != nullptr && blockIdx.x == 0 && it < TR_UNITS) trace[(role * TR_UNITS + it) * TR_EV + ev] = clock64();
 }
 
-// threads: RM/32 softmax warps | MMA issuer warp | leftover warp | TMA warp
-template <int KD, int RM>
-__global__ void __launch_bounds__(RM + 96, (RM == 64) ? (KD == 4 ? 3 : 4) : 2)
+// threads: SP * RM/32 softmax warps | MMA issuer warp | leftover warp | TMA warp
+// SP = 2 (two-tile units, T > 144: one CTA per SM anyway -- its S tile takes all of TMEM): two threads per query row, each
+// every other 32-column chunk of it through both passes; the partial row maxima / sums are swapped through shared memory
+// around a 64-thread named barrier.  Four softmax warps alone left the MUFU pipe 31 % busy there.
+template <int KD, int RM, int SP>
+__global__ void __launch_bounds__(RM * SP + 96, SP == 2 ? 1 : ((RM == 64) ? (KD == 4 ? 3 : 4) : 2))
 attn_tc5_fwd_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mQlo,
                     const __grid_constant__ CUtensorMap mKV, const __grid_constant__ CUtensorMap mO, const Tc5Geom gm,
                     bf16* __restrict__ out, float* __restrict__ lse, long long* __restrict__ trace) {
-  constexpr int dh = 16 * KD, RB = 32 * KD, NSW = RM / 32;
+  constexpr int dh = 16 * KD, RB = 32 * KD, NSQ = RM / 32, NSW = NSQ * SP;      // lane quadrants in use, softmax warps
   constexpr uint32_t LAY = sw_layout<KD>(), SBO = 8 * RB;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem);
+  float* xch = reinterpret_cast<float*>(smem + 256);                   // [2 = max | sum][SP][128]
   const uint32_t stage0 = smem_u32(smem + TC5_HDR);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int T = gm.T, Tk = gm.Tk, NT = gm.NT, NST = gm.nst;
@@ -179,7 +183,7 @@ attn_tc5_fwd_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constan
       mbar_init(bars->o_staged + s, NSW * NT);
     }
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, RM);
+    mbar_init(&bars->p_full, RM * SP);
     mbar_init(&bars->o_full, 1);
     mbar_init(&bars->t_empty, NSW);
     fence_barrier_init();
@@ -331,11 +335,19 @@ attn_tc5_fwd_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constan
       }
     }
   } else {
-    // ============================ softmax warps: thread = query row = TMEM lane ============================
-    const int row = warp * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ============================ softmax warps: thread = (half of a) query row = TMEM lane ============================
+    const int q = warp % NSQ, hf = warp / NSQ;                // lane quadrant ; which chunks / output columns (SP = 2)
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = gm.sl2;
     const int nch = gm.nch;
+    const int nmine = (nch - hf + SP - 1) / SP;               // this thread's chunks: hf, hf + SP, ...
+    // swap a partial row statistic with the thread that holds the other half of the row
+    auto swap_half = [&](int which, float mine) -> float {
+      xch[(which * SP + hf) * 128 + row] = mine;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      return xch[(which * SP + (hf ^ 1)) * 128 + row];
+    };
     int it = 0, s = 0;
     for (int u = blockIdx.x; u < gm.units; u += gridDim.x, ++it) {
       const int b = u / gm.h, hh = u - b * gm.h;
@@ -362,29 +374,34 @@ attn_tc5_fwd_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constan
           }
           mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
         };
-        tmem_ld32(trow, ra);
-        for (int c = 0; c < nch; c += 2) {
+        auto col = [&](int k) { return (uint32_t)((hf + SP * k) * 32); };      // first S column of this thread's k-th chunk
+        if (nmine > 0) tmem_ld32(trow + col(0), ra);
+        for (int k = 0; k < nmine; k += 2) {
           tmem_ld_wait32(ra);
-          if (c + 1 < nch) tmem_ld32(trow + (uint32_t)((c + 1) * 32), rb);
-          max32(ra, c);
-          if (c + 1 < nch) {
+          if (k + 1 < nmine) tmem_ld32(trow + col(k + 1), rb);
+          max32(ra, hf + SP * k);
+          if (k + 1 < nmine) {
             tmem_ld_wait32(rb);
-            if (c + 2 < nch) tmem_ld32(trow + (uint32_t)((c + 2) * 32), ra);
-            max32(rb, c + 1);
+            if (k + 2 < nmine) tmem_ld32(trow + col(k + 2), ra);
+            max32(rb, hf + SP * (k + 1));
           }
         }
+        if (SP == 2) mx = fmaxf(mx, swap_half(0, mx));
         if (tid == 0 && t == 0) tr(trace, 2, it, 1);
         // ---- pass 2: p = exp2(s c - m c), row sum, bf16 P back into TMEM over the S columns ----
+        // (with SP = 2 a thread overwrites only the S columns of its OWN chunks' first halves ... P of chunk c lands in
+        //  columns [16 c, 16 c + 16), which belong to chunk c / 2 of S: possibly the partner's, still unread.  So the
+        //  partner must have finished pass 1 -- the barrier inside swap_half above -- and pass 2 reads a chunk before any P
+        //  that overlaps a LATER chunk of either thread is stored: see the ordering note below.)
         const float ms = mx * sl2;
         float sum0 = 0.f, sum1 = 0.f;
-        auto exp32 = [&](uint32_t (&r)[32], int c) {
+        auto exp32 = [&](uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
           const int tv = T - c * 32;
           if (tv < 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j >= tv) r[j] = 0xff800000u;
           }
-          uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float p0 = ap::ex2(fmaf(__uint_as_float(r[2 * j]), sl2, -ms));
@@ -392,70 +409,98 @@ attn_tc5_fwd_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constan
             sum0 += p0; sum1 += p1;
             pk[j] = ap::pack2(p0, p1);
           }
-          tmem_st16(trow + (uint32_t)(c * 16), pk);
         };
-        tmem_ld32(trow, ra);
-        for (int c = 0; c < nch; c += 2) {
-          tmem_ld_wait32(ra);
-          if (c + 1 < nch) tmem_ld32(trow + (uint32_t)((c + 1) * 32), rb);
-          exp32(ra, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait32(rb);
-            if (c + 2 < nch) tmem_ld32(trow + (uint32_t)((c + 2) * 32), ra);
-            exp32(rb, c + 1);
+        if (SP == 1) {
+          uint32_t pk[16];
+          if (nmine > 0) tmem_ld32(trow, ra);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait32(ra);
+            if (c + 1 < nch) tmem_ld32(trow + (uint32_t)((c + 1) * 32), rb);
+            exp32(ra, c, pk);
+            tmem_st16(trow + (uint32_t)(c * 16), pk);
+            if (c + 1 < nch) {
+              tmem_ld_wait32(rb);
+              if (c + 2 < nch) tmem_ld32(trow + (uint32_t)((c + 2) * 32), ra);
+              exp32(rb, c + 1, pk);
+              tmem_st16(trow + (uint32_t)((c + 1) * 16), pk);
+            }
           }
+        } else {
+          // Two threads per row.  P of chunk c overwrites S columns [16 c, 16 c + 16) = the first (c even) or second (c odd)
+          // half of S chunk c / 2.  Chunks are taken in ascending order by both threads, a thread reads chunk c (and the
+          // partner chunk c +- 1) before either stores P(c) or P(c +- 1), and P(c) can only land on chunks <= c / 2, i.e. on
+          // chunks both threads have already read once c >= 2; for the first pair (c = 0, 1 -> S chunk 0) the store waits
+          // for a barrier after both threads have their first chunk in registers.
+          // (the chunk after next is requested before the barrier: it lies above every column a P store of this step can
+          //  touch -- chunk hf + 2k + 2 > k)
+          uint32_t pk[16];
+          if (nmine > 0) tmem_ld32(trow + col(0), ra);
+          for (int k = 0; k < nmine; k += 2) {
+            tmem_ld_wait32(ra);
+            if (k + 1 < nmine) tmem_ld32(trow + col(k + 1), rb);
+            // every chunk pair (2k, 2k + 1) is in registers on both sides before its P -- which overlaps S chunk k <= 2k --
+            // is stored: one 64-thread barrier per pair (the partner may have one chunk less: it still takes the barrier)
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            exp32(ra, hf + SP * k, pk);
+            tmem_st16(trow + (uint32_t)((hf + SP * k) * 16), pk);
+            if (k + 1 < nmine) {
+              tmem_ld_wait32(rb);
+              if (k + 2 < nmine) tmem_ld32(trow + col(k + 2), ra);
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              exp32(rb, hf + SP * (k + 1), pk);
+              tmem_st16(trow + (uint32_t)((hf + SP * (k + 1)) * 16), pk);
+            }
+          }
+          if (nmine < (nch + SP - 1) / SP) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // odd chunk count: keep the pair's barrier count equal
         }
         tmem_st_wait5();
         tc_fence_before();
         mbar_arrive(&bars->p_full);
         if (tid == 0 && t == 0) tr(trace, 2, it, 2);
-        const float sum = sum0 + sum1, inv = 1.f / sum;
+        float sum = sum0 + sum1;
+        if (SP == 2) sum += swap_half(1, sum);
+        const float inv = 1.f / sum;
         const int rg = t * 128 + row;                         // row inside the frame
-        if (lse != nullptr && rg < T) lse[((size_t)b * gm.h + hh) * T + rg] = ms + __log2f(sum);
+        if (lse != nullptr && rg < T && hf == 0) lse[((size_t)b * gm.h + hh) * T + rg] = ms + __log2f(sum);
         // ---- epilogue: O / sum -> bf16 -> staging (the dead Q tile) -> TMA store by the TMA warp ----
         mbar_wait(&bars->o_full, (uint32_t)(n & 1));
         tc_fence_after();
         if (tid == 0 && t == 0) tr(trace, 2, it, 3);
         const uint32_t ot = q_tile(s) + (uint32_t)(t * 128 * RB);
-        if (KD == 1) {
-          uint32_t o16[16];
-          tmem_ld16(trow + (uint32_t)gm.oc, o16);
-          tmem_ld_wait16(o16);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->t_empty);
+        // this thread's output columns: all dh (SP = 1) or half of them (SP = 2): CW 32-bit accumulator columns from c0
+        constexpr int CW = dh / SP, NCH = CW / 8;             // NCH 16-byte chunks of the staged row
+        const uint32_t oc0 = (uint32_t)(gm.oc + hf * CW);
+        uint32_t o[CW];
+        if (CW == 8) {
+          uint32_t t8[8];
+          tmem_ld8(trow + oc0, t8);
+          tmem_ld_wait8(t8);
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch)
-            sts128(ap::chunk_addr<KD>(ot, row, ch),
-                   ap::pack2(__uint_as_float(o16[8 * ch]) * inv, __uint_as_float(o16[8 * ch + 1]) * inv),
-                   ap::pack2(__uint_as_float(o16[8 * ch + 2]) * inv, __uint_as_float(o16[8 * ch + 3]) * inv),
-                   ap::pack2(__uint_as_float(o16[8 * ch + 4]) * inv, __uint_as_float(o16[8 * ch + 5]) * inv),
-                   ap::pack2(__uint_as_float(o16[8 * ch + 6]) * inv, __uint_as_float(o16[8 * ch + 7]) * inv));
+          for (int j = 0; j < CW; ++j) o[j] = t8[j % 8];
+        } else if (CW == 16) {
+          uint32_t t16[16];
+          tmem_ld16(trow + oc0, t16);
+          tmem_ld_wait16(t16);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) o[j] = t16[j % 16];
         } else {
-          tmem_ld32(trow + (uint32_t)gm.oc, ra);
-          if (KD == 4) tmem_ld32(trow + (uint32_t)(gm.oc + 32), rb);
+          tmem_ld32(trow + oc0, ra);
+          if (CW == 64) tmem_ld32(trow + oc0 + 32u, rb);
           tmem_ld_wait32(ra);
-          if (KD == 4) tmem_ld_wait32(rb);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->t_empty);
+          if (CW == 64) tmem_ld_wait32(rb);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            sts128(ap::chunk_addr<KD>(ot, row, ch),
-                   ap::pack2(__uint_as_float(ra[8 * ch]) * inv, __uint_as_float(ra[8 * ch + 1]) * inv),
-                   ap::pack2(__uint_as_float(ra[8 * ch + 2]) * inv, __uint_as_float(ra[8 * ch + 3]) * inv),
-                   ap::pack2(__uint_as_float(ra[8 * ch + 4]) * inv, __uint_as_float(ra[8 * ch + 5]) * inv),
-                   ap::pack2(__uint_as_float(ra[8 * ch + 6]) * inv, __uint_as_float(ra[8 * ch + 7]) * inv));
-          if (KD == 4) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              sts128(ap::chunk_addr<KD>(ot, row, 4 + ch),
-                     ap::pack2(__uint_as_float(rb[8 * ch]) * inv, __uint_as_float(rb[8 * ch + 1]) * inv),
-                     ap::pack2(__uint_as_float(rb[8 * ch + 2]) * inv, __uint_as_float(rb[8 * ch + 3]) * inv),
-                     ap::pack2(__uint_as_float(rb[8 * ch + 4]) * inv, __uint_as_float(rb[8 * ch + 5]) * inv),
-                     ap::pack2(__uint_as_float(rb[8 * ch + 6]) * inv, __uint_as_float(rb[8 * ch + 7]) * inv));
-          }
+          for (int j = 0; j < CW; ++j) o[j] = j < 32 ? ra[j % 32] : rb[j % 32];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->t_empty);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          sts128(ap::chunk_addr<KD>(ot, row, hf * NCH + ch),
+                 ap::pack2(__uint_as_float(o[8 * ch]) * inv, __uint_as_float(o[8 * ch + 1]) * inv),
+                 ap::pack2(__uint_as_float(o[8 * ch + 2]) * inv, __uint_as_float(o[8 * ch + 3]) * inv),
+                 ap::pack2(__uint_as_float(o[8 * ch + 4]) * inv, __uint_as_float(o[8 * ch + 5]) * inv),
+                 ap::pack2(__uint_as_float(o[8 * ch + 6]) * inv, __uint_as_float(o[8 * ch + 7]) * inv));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars->o_staged + s);
@@ -1219,27 +1264,31 @@ int attn_tc5_fwd(int B, int T, int h, int dh, const bf16* qkv, bf16* out, float*
   AMC_TRY(attn_make_map3(&mKV, qkv, B, T, 3 * g.d, dh, g.kbox_rows));
   AMC_TRY(attn_make_map3(&mO, out, B, T, g.d, dh, RM));
   long long* trace = tc5_trace_begin();
-#define AMC_TC5_FWD(KD, RM_)                                                                                          \
+#define AMC_TC5_FWD(KD, RM_, SP_)                                                                                     \
   do {                                                                                                                \
-    auto kern = attn_tc5_fwd_kernel<KD, RM_>;                                                                          \
+    auto kern = attn_tc5_fwd_kernel<KD, RM_, SP_>;                                                                     \
+    constexpr int threads = RM_ * SP_ + 96;                                                                           \
     AMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM_MAX));             \
     /* (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates TMEM, whatever its    \
        resources; the hardware does co-schedule such CTAs -- measured -- so the limits are applied here) */           \
-    int occ = tc5_ctas_per_sm((const void*)kern, RM_ + 96, sm, g.tmem_cols);                                          \
+    int occ = tc5_ctas_per_sm((const void*)kern, threads, sm, g.tmem_cols);                                           \
     if (getenv("AMC_TC5_OCC")) occ = atoi(getenv("AMC_TC5_OCC"));                                                     \
     const int grid = std::min(g.units, attn_sm_count() * occ);                                                        \
     if (trace) {                                                                                                      \
       cudaFuncAttributes fa;                                                                                          \
       cudaFuncGetAttributes(&fa, kern);                                                                               \
-      fprintf(stderr, "[tc5 fwd] grid %d occ %d smem %zu nst %d tmem %d o_sep %d units %d | regs %d static smem %zu local %zu maxdyn %d\n", \
-              grid, occ, sm, g.nst, g.tmem_cols, g.o_sep, g.units, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes); \
+      fprintf(stderr, "[tc5 fwd] grid %d occ %d threads %d smem %zu nst %d tmem %d o_sep %d units %d | regs %d static smem %zu local %zu maxdyn %d\n", \
+              grid, occ, threads, sm, g.nst, g.tmem_cols, g.o_sep, g.units, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes); \
     }                                                                                                                 \
-    kern<<<grid, RM_ + 96, sm, st>>>(mQ, mQlo, mKV, mO, g, out, lse, trace);                                                 \
+    kern<<<grid, threads, sm, st>>>(mQ, mQlo, mKV, mO, g, out, lse, trace);                                           \
   } while (0)
-#define AMC_TC5_FWD_KD(KD)                  \
-  do {                                      \
-    if (RM == 64) AMC_TC5_FWD(KD, 64);      \
-    else AMC_TC5_FWD(KD, 128);              \
+  /* two threads per row where a unit has two query tiles (T > 144: all of TMEM, one CTA per SM); AMC_TC5_SPLIT=0 off */ \
+  static const bool split_ok = [] { const char* e = getenv("AMC_TC5_SPLIT"); return !(e && e[0] == '0'); }();
+#define AMC_TC5_FWD_KD(KD)                                   \
+  do {                                                       \
+    if (RM == 64) AMC_TC5_FWD(KD, 64, 1);                    \
+    else if (g.NT == 2 && split_ok) AMC_TC5_FWD(KD, 128, 2); \
+    else AMC_TC5_FWD(KD, 128, 1);                            \
   } while (0)
   if (dh == 16) AMC_TC5_FWD_KD(1);
   else if (dh == 32) AMC_TC5_FWD_KD(2);

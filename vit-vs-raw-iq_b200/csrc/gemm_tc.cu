@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <initializer_list>
 
 #include "gemm_common.cuh"
@@ -862,7 +863,8 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
                   "gemm_bf16: fused LayerNorm epilogue needs N %% 32 == 0, N <= 256, residual, D16 and D32");
     const int bn_ln = g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256);
     // two epilogue warps per quadrant where the main loop is short (out-proj: K = d); FFN2 (K = F) keeps its third stage
-    return g.K <= 256 ? launch_row_bn<RE_LN, 8>(bn_ln, g, st) : launch_row_bn<RE_LN, 4>(bn_ln, g, st);
+    static const int ln8_maxk = [] { const char* e = getenv("AMC_LN8_MAXK"); return e ? atoi(e) : 256; }();
+    return g.K <= ln8_maxk ? launch_row_bn<RE_LN, 8>(bn_ln, g, st) : launch_row_bn<RE_LN, 4>(bn_ln, g, st);
   }
   if (row_ok) {
     if (e.mask_src && !e.res32 && e.D16 && !e.D32 && !e.bias && !e.relu && e.drop.p == 0.f)
