@@ -251,7 +251,10 @@ def test_layernorm_fwd_bwd(dt, M, d):
     assert relerr(dgamma, gd.grad) < tol and relerr(dbeta, bd.grad) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (333, 128, 1024), (4096, 256, 1024), (77, 64, 64), (513, 96, 128)])
+# N <= 256: double-buffered accumulator, two epilogue warps per quadrant when K <= 256 (out-proj), one otherwise (FFN2);
+# 256 < N <= 512 (d_model 384 / 512): one 512-column single-buffered accumulator fed by two N = 256 MMAs per k-step
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (333, 128, 1024), (4096, 256, 1024), (77, 64, 64), (513, 96, 128),
+                                   (1000, 512, 512), (333, 384, 384), (2500, 512, 2048), (130, 384, 1536), (129, 288, 64)])
 def test_gemm_fused_layernorm_epilogue(M, N, K):
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
     A = torch.randn(M, K, device=DEV, generator=g).bfloat16()

@@ -153,6 +153,62 @@ __global__ void store_latency(const __grid_constant__ CUtensorMap map, long long
   }
 }
 
+// ---- 1-D bulk copies (cp.async.bulk, no tensor map): what the T <= 16 attention kernels use.  A "frame" is T = 9 token rows
+// of q|k|v (1536 B each) in and 9 rows of 512 B out.  rows = 1: one copy per row (shared-memory pitch padded by 16 B);
+// rows = 0: one copy per frame (the global layout itself padded, so the block is contiguous on both sides).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(256, 2) bulk_frames(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int frames, int per_row,
+                                                      int F) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const int T = 9, RIN = 1536, ROUT = 512, PIN = RIN + 16, POUT = ROUT + 16;
+  const uint32_t in0 = s_u32(smem + 128), in_bytes = (uint32_t)(F * T * PIN), out0 = in0 + 2 * in_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  const size_t gin = per_row ? RIN : PIN, gout = per_row ? ROUT : POUT;     // global row pitch
+  auto load = [&](int f0, int buf) {
+    const int nf = min(F, frames - f0);
+    if (per_row) {
+      if (warp == 0 && lane == 0) mbar_expect_tx(bars + buf, (uint32_t)(nf * T * RIN));
+      if (lane == 0)
+        for (int r = warp; r < nf * T; r += nw) bulk_g2s(in0 + buf * in_bytes + r * PIN, src + ((size_t)f0 * T + r) * gin, RIN, bars + buf);
+    } else if (warp == 0 && lane == 0) {
+      mbar_expect_tx(bars + buf, (uint32_t)(nf * T * PIN));
+      bulk_g2s(in0 + buf * in_bytes, src + (size_t)f0 * T * gin, (uint32_t)(nf * T * PIN), bars + buf);
+    }
+  };
+  const int stride = gridDim.x * F;
+  int f0 = blockIdx.x * F;
+  if (f0 < frames) load(f0, 0);
+  for (uint32_t it = 0; f0 < frames; f0 += stride, ++it) {
+    const int nf = min(F, frames - f0);
+    if (f0 + stride < frames) load(f0 + stride, (it + 1) & 1);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    mbar_wait(bars + (it & 1), (it >> 1) & 1);
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (per_row) {
+      if (lane == 0) {
+        for (int r = warp; r < nf * T; r += nw) bulk_s2g(dst + ((size_t)f0 * T + r) * gout, out0 + r * POUT, ROUT);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (warp == 0 && lane == 0) {
+      bulk_s2g(dst + (size_t)f0 * T * gout, out0, (uint32_t)(nf * T * POUT));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main() {
   EncodeTiledFn enc = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -166,6 +222,28 @@ int main() {
   cudaMemset(src, 1, bytes); cudaMemset(dst, 0, bytes);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+
+  {
+    const int frames = 32768, F = 3;
+    uint8_t *a, *b;
+    cudaMalloc(&a, (size_t)frames * 9 * 1552); cudaMalloc(&b, (size_t)frames * 9 * 528);
+    cudaMemset(a, 1, (size_t)frames * 9 * 1552);
+    const size_t sm = 256 + 2 * F * 9 * 1552 + F * 9 * 528;
+    cudaFuncSetAttribute(bulk_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int per_row : {1, 0}) {
+      float best = 1e9;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        bulk_frames<<<2 * sms, 256, sm>>>(a, b, frames, per_row, F);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+      }
+      cudaError_t e = cudaGetLastError();
+      printf("bulk 1-D copies, T = 9 frames (13.8 KB in, 4.6 KB out), %s: %.1f us for %d frames = %.0f cycles per frame per SM @1.9GHz, %.0f GB/s %s\n",
+             per_row ? "one copy per ROW " : "one copy per FRAME", best * 1e3, frames, best * 1e-3 * 1.9e9 / (frames / (double)sms),
+             frames * 9.0 * 2048 / best / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+  }
   for (int rb : {32, 64, 128, 256}) {
     P p; p.B = B; p.T = T; p.cols = cols; p.rb = rb; p.heads = (2 * d) / rb; p.units = B * p.heads; p.nst = 3; p.tiles = 3;
     p.tile_bytes = ((144 * rb) + 1023) / 1024 * 1024;

@@ -73,7 +73,8 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* mapA, const CUt
       mbar_expect_tx(full_bar + stage, STAGE_BYTES);
       if (MODE_MN == 0) {
         tma_load_2d(mapA, full_bar + stage, sa, kb * BK, m0);       // box {64 k, 128 rows}
-        tma_load_2d(mapB, full_bar + stage, sb, kb * BK, n0);       // box {64 k, BN rows}
+        tma_load_2d(mapB, full_bar + stage, sb, kb * BK, n0);       // box {64 k, min(BN, 256) rows}
+        if (BN > 256) tma_load_2d(mapB, full_bar + stage, sb + 256 * BK * 2, kb * BK, n0 + 256);
       } else {
 #pragma unroll
         for (int j = 0; j < BM / 64; ++j)                            // boxes {64 m, 64 tokens}
@@ -92,7 +93,9 @@ __device__ __forceinline__ void mma_loop(const TcParams& p, unsigned char* smem,
                                          uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                          uint32_t tmem_base) {
   constexpr int A_BYTES = BM * BK * 2, STAGE_BYTES = A_BYTES + BN * BK * 2;
-  constexpr uint32_t idesc = make_idesc(BM, BN, MODE_MN);
+  constexpr int UN = BN > 256 ? 256 : BN;          // UMMA N (<= 256): a 512-column tile is two MMAs per k-step
+  constexpr int NACC = BN > 256 ? 1 : 2;           // accumulator stages in TMEM (512 columns in all)
+  constexpr uint32_t idesc = make_idesc(BM, UN, MODE_MN);
   const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
   int stage = 0;
   uint32_t phase = 0;
@@ -120,12 +123,15 @@ __device__ __forceinline__ void mma_loop(const TcParams& p, unsigned char* smem,
           bdesc = make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024);
         }
         umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        if (BN > 256)          // (K-major only: the row kernel) second half of the N columns: B rows 256.. of the stage
+          umma_bf16(tmem_d + 256u, adesc, make_smem_desc(sb + 256 * BK * 2 + k * (UMMA_K * 2), 16, 1024), idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
       }
       umma_commit(empty_bar + stage);            // frees the smem stage when the MMAs retire
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     umma_commit(tfull_bar + as);                 // accumulator complete -> epilogue
-    if (++as == 2) { as = 0; aphase ^= 1; }
+    if (++as == NACC) { as = 0; aphase ^= 1; }
   }
 }
 
@@ -316,7 +322,7 @@ struct RowParams {
 template <int BN, int RE, int W = 8> struct RowCfg {
   // (the two-warps-per-quadrant LayerNorm epilogue pays for its second set of slabs with one operand stage)
   static constexpr bool LN8 = (RE == RE_LN && W == 8);
-  static constexpr int STAGES = LN8 ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
+  static constexpr int STAGES = BN > 256 ? 2 : (LN8 ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   // bf16-output epilogues are instruction-heavy (dropout hash, mask tests, packing): two warps per TMEM
   // lane quadrant alternate over the 32-column chunks; the fp32 / LayerNorm epilogues keep one warp per
@@ -343,7 +349,7 @@ template <int BN, int RE, int W = 8> struct RowCfg {
   static constexpr int CS_OFF = BAR_OFF + 512;             // fp32 column accumulator (N <= 2048), bf16-output variants
   static constexpr int CS_BYTES = WIDE ? 0 : 8192;
   static constexpr int SMEM_BYTES = CS_OFF + CS_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = BN > 256 ? BN : 2 * BN;      // 512-column tiles: single-buffered accumulator
   static constexpr int THREADS = 64 + 32 * NEPI;
 };
 
@@ -699,7 +705,7 @@ gemm_tc_row_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + as);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == (BN > 256 ? 1 : 2)) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();
   }
@@ -793,7 +799,7 @@ int launch_row(const GemmArgs& g, cudaStream_t st) {
   const Epi& e = g.epi;
   CUtensorMap mapA, mapB, mapIn, mapO16, mapO32, mapXh;
   AMC_TRY(make_map(&mapA, g.A, g.M, g.K, g.lda, BK, BM));
-  AMC_TRY(make_map(&mapB, g.B, g.N, g.K, g.ldb, BK, BN));
+  AMC_TRY(make_map(&mapB, g.B, g.N, g.K, g.ldb, BK, BN > 256 ? 256 : BN));
   mapIn = mapA; mapO16 = mapA; mapO32 = mapA; mapXh = mapA;      // placeholders for unused descriptors
   if (RE == RE_MASK) AMC_TRY(make_map_ex(&mapIn, e.mask_src, g.M, g.N, e.ldmask, 32, 32, false, true));
   if (RE == RE_RES32 || RE == RE_LN) AMC_TRY(make_map_ex(&mapIn, e.res32, g.M, g.N, e.ldres, 32, 32, true, false));
@@ -858,9 +864,12 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t st) {
                       (!e.res32 || (al16(e.res32) && e.ldres % 4 == 0)) &&
                       (!e.mask_src || (al16(e.mask_src) && e.ldmask % 8 == 0)) && (!e.bias || al16(e.bias));
   if (e.ln_gamma) {
-    AMC_CHECK_ARG(row_ok && e.res32 && e.D16 && e.D32 && !e.mask_src && !e.relu && g.N <= 256 && al16(e.ln_gamma) &&
+    AMC_CHECK_ARG(row_ok && e.res32 && e.D16 && e.D32 && !e.mask_src && !e.relu && g.N <= 512 && al16(e.ln_gamma) &&
                       al16(e.ln_beta) && (!e.ln_xhat || al16(e.ln_xhat)),
-                  "gemm_bf16: fused LayerNorm epilogue needs N %% 32 == 0, N <= 256, residual, D16 and D32");
+                  "gemm_bf16: fused LayerNorm epilogue needs N %% 32 == 0, N <= 512, residual, D16 and D32");
+    // d in (256, 512]: the row spans two N = 256 MMAs and all 512 TMEM columns (accumulator single-buffered: the epilogue of
+    // a tile no longer overlaps the next tile's main loop, still cheaper than a separate LayerNorm pass over HBM)
+    if (g.N > 256) return launch_row<512, RE_LN, 4>(g, st);
     const int bn_ln = g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256);
     // two epilogue warps per quadrant where the main loop is short (out-proj: K = d); FFN2 (K = F) keeps its third stage
     static const int ln8_maxk = [] { const char* e = getenv("AMC_LN8_MAXK"); return e ? atoi(e) : 256; }();
