@@ -256,7 +256,9 @@ template <typename E> int gemm(const GemmArgs& g, cudaStream_t st) {
 inline int pick_split_k(int Mo, int No, int K) {
   const int tiles = ceil_div(Mo, 128) * ceil_div(No, 128);
   int s = std::max(1, (148 * 2) / std::max(tiles, 1));
-  s = std::min(s, std::max(1, K / 256));
+  // tokens per split: every split pays a full tile of fp32 atomics, so short K ranges (small batches) take fewer splits
+  static const int min_k = [] { const char* e = getenv("AMC_WGRAD_MIN_K"); return e ? std::max(64, atoi(e)) : 256; }();
+  s = std::min(s, std::max(1, K / min_k));
   return s;
 }
 
