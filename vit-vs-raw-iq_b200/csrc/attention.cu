@@ -9,7 +9,8 @@
 // tests/test_gpu_ops.py (the shape lists there name the branch each case exercises):
 //   T > 288                                   attn_long.cu   flash-style tiles (conv1d embedding, T = 1025)
 //   bf16, T <= 16, dh in {16,32,64}           attn_mma_*     frames x heads packed per CTA (ViT p16: T = 9)
-//   bf16, 49 <= T <= 272, dh in {16,32,64}    attn_tc5.cu    tcgen05 / TMEM, where it is the faster kernel (T > 80 or dh = 64)
+//   bf16, 49 <= T <= 272, dh in {16,32,64}    attn_tc5.cu    tcgen05 / TMEM, where it is the faster kernel, per direction (forward: T > 80 or
+//                                                            dh = 64; backward: dh = 32 at T > 80, dh = 64): tc5_preferred()
 //   bf16, 16 < T <= 288, dh in {16,32,64}     attn_tiles.cu  mma.sync tiles (backward: while its tiles fit, i.e. not dh = 64, T > 176)
 //   T <= 32, dh <= 32, h T <= 256             attn_frames_*  SIMT, several frames per CTA (fp32 parity path; bf16 odd head dims)
 //   anything else (T <= 288, dh <= 128)       attn_fwd/bwd_kernel  SIMT, one CTA per (frame, head): fp32, head dims 48 / 96 / 128,

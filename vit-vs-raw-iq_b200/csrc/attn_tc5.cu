@@ -21,7 +21,9 @@
 //   No shuffles, no ldmatrix, no per-element shared-memory traffic on the main rows.
 // TMEM columns: S at [0, Tk), P aliases S at [0, Tk/2) (bf16 pairs), O at [OC, OC + dh) inside the dead S columns:
 // 128 / 256 columns per CTA for T <= 80 / <= 144, so 4 / 2 CTAs share an SM and one CTA's MMA and copy phases overlap
-// the other's softmax.
+// the other's softmax.  Two-tile units (T > 144) take all 512 columns -- one CTA per SM -- and run TWO threads per query
+// row (SP = 2: 8 softmax warps; partial maxima / sums swapped through shared memory, P stores ordered against the
+// partner's S reads by a 64-thread named barrier per chunk pair).
 #ifdef TC5_BACKOFF
 #define AMC_MBAR_BACKOFF_NS TC5_BACKOFF
 #endif
