@@ -279,6 +279,20 @@ def run_reference_arm(args, w, wname):
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(table, workload, kernel_class, frames, default_frames):
+    """DRAM bytes per launch of `kernel_class` from profiles/ncu_traffic.json -> (bytes or None, where they come from).
+    An entry records the frames per launch of its `ncu --set full` capture (absent = the workload's bench batch); when this
+    run's batch differs the figure is scaled linearly (every kernel class here moves bytes in proportion to the frames)."""
+    ent = table.get(workload, {}).get(kernel_class, {})
+    traffic = ent.get("dram_bytes_per_launch")
+    if traffic is None:
+        return None, None
+    cap = ent.get("frames") or default_frames
+    if cap != frames:
+        return traffic * frames / cap, f"ncu capture at {cap} frames per launch, scaled by {frames}/{cap}"
+    return traffic, f"ncu capture at this launch size ({ent.get('report')})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,18 +476,10 @@ def main():
 
     table = [class_roofline(k, v) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if v["bytes"] or v["flops"]]
     dom = table[0]
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # written by tools/ncu_summary.py from `ncu --set full`
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        ent = tj.get(args.workload, {}).get(dom["kernel"], {})
-        traffic = ent.get("dram_bytes_per_launch")
-        cap_frames = ent.get("frames") or w["batch"]          # frames per launch of the ncu capture (default: the bench batch)
-        if traffic is not None and cap_frames != B:
-            traffic_note = f"ncu capture at {cap_frames} frames per launch, scaled by {B}/{cap_frames}"
-            traffic = traffic * B / cap_frames
-        elif traffic is not None:
-            traffic_note = f"ncu capture at this launch size ({ent.get('report')})"
+        traffic, traffic_note = ncu_traffic(json.load(open(tpath)), args.workload, dom["kernel"], B, w["batch"])
     roofline = {k: dom[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
     if traffic is not None:
         roofline["traffic_source"] = traffic_note

@@ -83,3 +83,47 @@ def test_vendored_reference_is_a_byte_copy_and_runs(tmp_path):
     l0 = ref.step(x, y).item()
     l1 = ref.step(x, y).item()
     assert math.isfinite(l0) and math.isfinite(l1)
+
+
+def test_roofline_traffic_is_scaled_to_the_run_batch():
+    """`roofline.traffic` comes from an ncu capture that may have been taken at another batch: bench.py scales it and says so."""
+    import bench
+    table = {"vit_p16_d256_L6": {"gemm_wgrad": {"dram_bytes_per_launch": 100.0, "report": "a.csv", "frames": None},
+                                 "attn_fwd": {"dram_bytes_per_launch": 50.0, "report": "b.csv", "frames": 8192}}}
+    assert bench.ncu_traffic(table, "vit_p16_d256_L6", "gemm_wgrad", 32768, 32768) == (100.0, "ncu capture at this launch size (a.csv)")
+    got, note = bench.ncu_traffic(table, "vit_p16_d256_L6", "attn_fwd", 32768, 32768)
+    assert got == 200.0 and "8192" in note and "scaled" in note
+    got, note = bench.ncu_traffic(table, "vit_p16_d256_L6", "gemm_wgrad", 4096, 32768)      # --batch 4096 run
+    assert got == 12.5 and "scaled" in note
+    assert bench.ncu_traffic(table, "vit_p16_d256_L6", "ln_bwd", 32768, 32768) == (None, None)
+    assert bench.ncu_traffic(table, "other", "gemm_wgrad", 1, 1) == (None, None)
+
+
+def test_ncu_full_summary_reads_the_raw_csv_made_on_the_gpu_box(tmp_path, monkeypatch):
+    """tools/ncu_summary.py full: per-kernel aggregation of the `ncu --page raw --csv` text (the reports themselves are too
+    big to bring back from the GPU box) and the class table bench.py reads; a new capture replaces a class's old entry."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import importlib
+    ns = importlib.import_module("ncu_summary")
+    csv_text = (
+        '"ID","Kernel Name","gpu__time_duration.sum","dram__bytes_read.sum","dram__bytes_write.sum","launch__registers_per_thread"\n'
+        '"","","us","Mbyte","Mbyte","register/thread"\n'
+        '"0","void amc::<unnamed>::gemm_tc_kernel<256, 1, 0>(CUtensorMap_st, int)","100","300","100","128"\n'
+        '"1","void amc::<unnamed>::gemm_tc_kernel<256, 1, 0>(CUtensorMap_st, int)","120","320","80","128"\n'
+        '"2","void amc::<unnamed>::attn_tc5_bwd_kernel<2>(CUtensorMap_st)","300","340","170","156"\n')
+    src = tmp_path / "cap.csv"
+    src.write_text(csv_text)
+    monkeypatch.setattr(ns, "ROOT", str(tmp_path))
+    os.makedirs(tmp_path / "profiles")
+    (tmp_path / "profiles" / "ncu_traffic.json").write_text(json.dumps(
+        {"w": {"gemm_wgrad": {"dram_bytes_per_launch": 1.0, "launches": 9, "kernels": ["old"], "report": "old.ncu-rep"}}}))
+    out = tmp_path / "sum.json"
+    ns.full(str(src), str(out), "w", 4096)
+    res = json.loads(out.read_text())["kernels"]
+    k = res["gemm_tc_kernel<256, 1, 0>"]
+    assert k["launches"] == 2 and abs(k["duration_us_per_launch"] - 110.0) < 1e-6
+    assert abs(k["dram_bytes_per_launch"] - 400e6) < 1.0
+    tj = json.loads((tmp_path / "profiles" / "ncu_traffic.json").read_text())["w"]
+    assert tj["gemm_wgrad"]["report"] == "cap.csv" and tj["gemm_wgrad"]["launches"] == 2 and tj["gemm_wgrad"]["frames"] == 4096
+    assert abs(tj["gemm_wgrad"]["dram_bytes_per_launch"] - 400e6) < 1.0
+    assert tj["attn_bwd"]["kernels"] == ["attn_tc5_bwd_kernel<2>"] and abs(tj["attn_bwd"]["dram_bytes_per_launch"] - 510e6) < 1.0
