@@ -248,7 +248,9 @@ class HostPipeline:
         self.i = 0
         self.batch = src_shape[0]
 
-    def step(self, src_host: torch.Tensor, labels_host: torch.Tensor):
+    def step(self, src_host: torch.Tensor, labels_host: torch.Tensor, sync: bool = False):
+        """``sync=True``: wait for THIS step and return its loss (the reference's ``loss.item()`` semantics, train.py:274);
+        the default returns the previous step's loss so that the next batch's H2D copy overlaps this step's compute."""
         k = self.i & 1
         xs, ys = self.bufs[k]
         cur = torch.cuda.current_stream(self.t.dev)
@@ -264,6 +266,11 @@ class HostPipeline:
         _lib.check(_lib.lib.amc_zero(self.t.stats.data_ptr(), 8, cur.cuda_stream), "amc_zero")
         self.t.frames_seen = 0
         self.loss_evt[k].record(cur)
+        if sync:
+            self.loss_evt[k].synchronize()
+            _check_loss(float(self.loss_host[k][0]))
+            self.i += 1
+            return float(self.loss_host[k][0]) / self.batch
         prev = None
         if self.i > 0:
             self.loss_evt[1 - k].synchronize()
